@@ -1,0 +1,373 @@
+// flash_fwd_sm100.cu — Blackwell (sm_100a) fused attention forward.
+//
+//   O = softmax(Q K^T / sqrt(d) + mask) V,   LSE = ln sum exp(.)      (reference semantics:
+//   /root/reference/csrc/flash_attn/src/flash_fwd_kernel.h:23-789, mask.h:20-72)
+//
+// Data path (nothing here resembles the reference's ld.global -> st.shared -> ldmatrix -> mma.sync
+// pipeline; it is designed for the B200 SM):
+//   * Q, K, V tiles are fetched by TMA (cp.async.bulk.tensor, 128-byte swizzle) straight into shared
+//     memory; out-of-range rows are zero-filled by the TMA unit, so ragged lengths need no special
+//     load path.
+//   * S = Q K^T and O += P V run on the 5th-gen tensor cores (tcgen05.mma, kind::f16) issued by one
+//     thread; S and O live in tensor memory (TMEM), P is written back to TMEM as the A operand of PV
+//     (V is consumed in place as an MN-major B operand — no transpose anywhere).
+//   * The online softmax runs with one thread per query row (tcgen05.ld 32x32b), so row max / row sum
+//     need no cross-thread reduction at all.
+//
+// This file holds the general kernel "flash_fwd_kernel_sm100_g": one 128-row Q tile per CTA, any
+// sequence lengths, causal, GQA, varlen, d in {64,128}, fp16/bf16.
+#include "fa_common.h"
+#include "sm100_ptx.cuh"
+
+namespace fa100 {
+
+struct FwdParams {
+    void* o;
+    float* lse;
+    const int* cu_q;
+    const int* cu_k;
+    int b, sq, sk, h, h_k, hratio;
+    int is_causal;
+    float scale;       // 1/sqrt(d)
+    float scale_log2;  // log2(e)/sqrt(d)
+};
+
+constexpr int kBlockM = 128;  // query rows per tile  (= TMEM lanes = UMMA M)
+constexpr int kBlockN = 128;  // key rows per tile    (= UMMA N of S, K extent of PV)
+
+template <int D> struct FwdSmemG {
+    static constexpr int kSlab = kBlockM * 128;             // one 64-column slab of a 128-row tile (16 KB)
+    static constexpr int kTile = kBlockM * D * 2;           // one full tile
+    static constexpr int kStages = 2;
+    static constexpr int kOffQ = 0;
+    static constexpr int kOffK = kTile;
+    static constexpr int kOffV = kOffK + kStages * kTile;
+    static constexpr int kOffBar = kOffV + kStages * kTile;
+    static constexpr int kBytes = kOffBar + 256 + 1024;     // + barriers + alignment slack
+};
+
+// TMEM column map (512 columns allocated; 1 CTA per SM)
+constexpr uint32_t kTmemS = 0;     // 128 fp32 columns
+constexpr uint32_t kTmemP = 128;   // 64 columns (128 x 16-bit)
+constexpr uint32_t kTmemO = 256;   // D fp32 columns
+
+template <int D, bool kBf16>
+__global__ void __launch_bounds__(192, 1)
+flash_fwd_kernel_sm100_g(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                         const __grid_constant__ CUtensorMap tmV, const FwdParams p) {
+    using L = FwdSmemG<D>;
+    constexpr int kSlabs = D / 64;
+
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5;
+    const int lane = tid & 31;
+    const int m0 = blockIdx.x * kBlockM;
+    const int bidh = blockIdx.y;
+    const int bidb = blockIdx.z;
+    const int bidh_k = bidh / p.hratio;
+
+    // ---- per-sequence geometry (BlockInfo equivalent, block_info.h:3-27, with 64-bit row math) ----
+    int q_row0, k_row0, sq_b, sk_b, tma_b;
+    if (p.cu_q != nullptr) {
+        q_row0 = p.cu_q[bidb];
+        sq_b = p.cu_q[bidb + 1] - q_row0;
+        k_row0 = p.cu_k[bidb];
+        sk_b = p.cu_k[bidb + 1] - k_row0;
+        tma_b = 0;
+    } else {
+        q_row0 = 0; k_row0 = 0; sq_b = p.sq; sk_b = p.sk; tma_b = bidb;
+    }
+    if (m0 >= sq_b) return;
+    const int causal_off = sk_b - sq_b;  // keep (i,j) iff j <= i + causal_off
+    int kv_end = sk_b;
+    if (p.is_causal) kv_end = min(sk_b, max(0, m0 + kBlockM + causal_off));
+    const int n_blocks = (kv_end + kBlockN - 1) / kBlockN;
+
+    const int64_t o_row_base = (p.cu_q != nullptr) ? (int64_t)q_row0 : (int64_t)bidb * p.sq;
+    float* lse_row = p.lse + ((int64_t)bidb * p.h + bidh) * p.sq;
+
+    if (n_blocks == 0) {
+        // every row of this tile is fully masked: O = 0, LSE = 0 (flash_fwd_kernel.h:275, :717-730, :766-785)
+        for (int idx = tid; idx < kBlockM * (D / 8); idx += blockDim.x) {
+            const int r = idx / (D / 8), c = idx % (D / 8);
+            if (m0 + r < sq_b) {
+                uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.o) +
+                                                      ((o_row_base + m0 + r) * p.h + bidh) * D) + c;
+                *dst = make_uint4(0, 0, 0, 0);
+            }
+        }
+        if (tid < kBlockM && m0 + tid < sq_b) lse_row[m0 + tid] = 0.f;
+        return;
+    }
+
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* sQ = smem + L::kOffQ;
+    uint8_t* sK = smem + L::kOffK;
+    uint8_t* sV = smem + L::kOffV;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::kOffBar);
+    uint64_t* bar_q = bars + 0;
+    uint64_t* bar_kv_full = bars + 1;   // [2]
+    uint64_t* bar_kv_empty = bars + 3;  // [2]
+    uint64_t* bar_s_full = bars + 5;
+    uint64_t* bar_s_empty = bars + 6;
+    uint64_t* bar_p_full = bars + 7;
+    uint64_t* bar_o_done = bars + 8;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
+
+    if (warp == 4) {
+        if (lane == 0) {
+            mbar_init(bar_q, 1);
+            mbar_init(&bar_kv_full[0], 1); mbar_init(&bar_kv_full[1], 1);
+            mbar_init(&bar_kv_empty[0], 1); mbar_init(&bar_kv_empty[1], 1);
+            mbar_init(bar_s_full, 1);
+            mbar_init(bar_s_empty, kBlockM);
+            mbar_init(bar_p_full, kBlockM);
+            mbar_init(bar_o_done, 1);
+            fence_barrier_init();
+            tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV);
+        }
+        __syncwarp();
+        tmem_alloc<512>(tmem_slot);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 4) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            mbar_arrive_expect_tx(bar_q, L::kTile);
+            for (int s = 0; s < kSlabs; ++s)
+                tma_load_4d(sQ + s * L::kSlab, &tmQ, bar_q, s * 64, bidh, q_row0 + m0, tma_b);
+            for (int j = 0; j < n_blocks; ++j) {
+                const int st = j & 1;
+                mbar_wait(&bar_kv_empty[st], ((j >> 1) & 1) ^ 1);
+                mbar_arrive_expect_tx(&bar_kv_full[st], 2 * L::kTile);
+                for (int s = 0; s < kSlabs; ++s)
+                    tma_load_4d(sK + st * L::kTile + s * L::kSlab, &tmK, &bar_kv_full[st], s * 64, bidh_k,
+                                k_row0 + j * kBlockN, tma_b);
+                for (int s = 0; s < kSlabs; ++s)
+                    tma_load_4d(sV + st * L::kTile + s * L::kSlab, &tmV, &bar_kv_full[st], s * 64, bidh_k,
+                                k_row0 + j * kBlockN, tma_b);
+            }
+        }
+    } else if (warp == 5) {
+        // ===================== MMA issuer (one thread) =====================
+        if (lane == 0) {
+            constexpr uint32_t idesc_s = make_idesc(kBf16, kBlockM, kBlockN, false, false);
+            constexpr uint32_t idesc_pv = make_idesc(kBf16, kBlockM, D, false, true);
+            const uint32_t q_addr = smem_u32(sQ);
+            mbar_wait(bar_q, 0);
+            for (int j = 0; j < n_blocks; ++j) {
+                const int st = j & 1;
+                const uint32_t k_addr = smem_u32(sK + st * L::kTile);
+                const uint32_t v_addr = smem_u32(sV + st * L::kTile);
+                mbar_wait(&bar_kv_full[st], (j >> 1) & 1);
+                mbar_wait(bar_s_empty, (j & 1) ^ 1);
+                tc_fence_after();
+                // S[128 x 128] = Q[128 x D] K[128 x D]^T : both K-major, 16 elements (32 B) per MMA step
+#pragma unroll
+                for (int kk = 0; kk < D / 16; ++kk) {
+                    const uint32_t off = (kk >> 2) * L::kSlab + (kk & 3) * 32;
+                    umma_ss(tmem_base + kTmemS, make_smem_desc(q_addr + off, 16, 1024),
+                            make_smem_desc(k_addr + off, 16, 1024), idesc_s, kk > 0);
+                }
+                tc_commit(bar_s_full);
+                mbar_wait(bar_p_full, j & 1);
+                tc_fence_after();
+                // O[128 x D] += P[128 x 128] V[128 x D] : P from TMEM, V MN-major (16 key rows = 2048 B per step)
+#pragma unroll
+                for (int kk = 0; kk < kBlockN / 16; ++kk) {
+                    umma_ts(tmem_base + kTmemO, tmem_base + kTmemP + kk * 8,
+                            make_smem_desc(v_addr + kk * 2048, L::kSlab, 1024), idesc_pv, (j > 0 || kk > 0));
+                }
+                tc_commit(&bar_kv_empty[st]);
+                tc_commit(bar_o_done);
+            }
+        }
+    } else {
+        // ===================== softmax / correction / epilogue: one thread per query row =====================
+        const int row = m0 + tid;
+        const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+        const uint32_t tS = tmem_base + lane_base + kTmemS;
+        const uint32_t tP = tmem_base + lane_base + kTmemP;
+        const uint32_t tO = tmem_base + lane_base + kTmemO;
+        // last visible key column for this row
+        int col_limit = sk_b - 1;
+        if (p.is_causal) col_limit = min(col_limit, row + causal_off);
+        float m_run = -INFINITY, l_run = 0.f;
+        const float c2 = p.scale_log2;
+
+        for (int j = 0; j < n_blocks; ++j) {
+            const int n0 = j * kBlockN;
+            mbar_wait(bar_s_full, j & 1);
+            tc_fence_after();
+            float s[kBlockN];
+#pragma unroll
+            for (int c = 0; c < kBlockN / 32; ++c)
+                tmem_ld32(tS + c * 32, *reinterpret_cast<uint32_t(*)[32]>(&s[c * 32]));
+            tmem_wait_ld();
+            tc_fence_before();
+            mbar_arrive(bar_s_empty);
+
+            const bool need_mask = (n0 + kBlockN > sk_b) || (p.is_causal && (n0 + kBlockN - 1 > m0 + causal_off));
+            if (need_mask) {
+                const int lim = col_limit - n0;
+#pragma unroll
+                for (int c = 0; c < kBlockN; ++c)
+                    if (c > lim) s[c] = -INFINITY;
+            }
+            float mx = s[0];
+#pragma unroll
+            for (int c = 1; c < kBlockN; ++c) mx = fmaxf(mx, s[c]);
+            const float m_new = fmaxf(m_run, mx);
+            const float m_safe = (m_new == -INFINITY) ? 0.f : m_new;
+            const float alpha = fast_exp2((m_run - m_safe) * c2);
+            const float neg = -m_safe * c2;
+            float sum = 0.f;
+#pragma unroll
+            for (int c = 0; c < kBlockN; ++c) {
+                s[c] = fast_exp2(fmaf(s[c], c2, neg));
+                sum += s[c];
+            }
+            l_run = l_run * alpha + sum;
+            m_run = m_new;
+
+            if (j > 0) {
+                mbar_wait(bar_o_done, (j - 1) & 1);
+                tc_fence_after();
+                if (__any_sync(0xffffffffu, alpha != 1.f)) {
+#pragma unroll
+                    for (int c = 0; c < D / 32; ++c) {
+                        uint32_t o[32];
+                        tmem_ld32(tO + c * 32, o);
+                        tmem_wait_ld();
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+                        tmem_st32(tO + c * 32, o);
+                    }
+                }
+            }
+#pragma unroll
+            for (int c = 0; c < kBlockN / 64; ++c) {
+                uint32_t pk[32];
+#pragma unroll
+                for (int i = 0; i < 32; ++i) pk[i] = pack2<kBf16>(s[c * 64 + 2 * i], s[c * 64 + 2 * i + 1]);
+                tmem_st32(tP + c * 32, pk);
+            }
+            tmem_wait_st();
+            tc_fence_before();
+            mbar_arrive(bar_p_full);
+        }
+
+        // ---- epilogue: O / l -> 16-bit -> smem (reuses the Q tile) -> coalesced global stores ----
+        mbar_wait(bar_o_done, (n_blocks - 1) & 1);
+        tc_fence_after();
+        const float inv_l = (l_run > 0.f) ? (1.f / l_run) : 0.f;
+        uint8_t* sO = sQ;  // all S MMAs have retired (o_done covers every earlier tcgen05.mma)
+#pragma unroll
+        for (int c = 0; c < D / 32; ++c) {
+            uint32_t o[32];
+            tmem_ld32(tO + c * 32, o);
+            tmem_wait_ld();
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {  // 4 x 16-byte chunks (8 values each)
+                uint4 v;
+                v.x = pack2<kBf16>(__uint_as_float(o[g * 8 + 0]) * inv_l, __uint_as_float(o[g * 8 + 1]) * inv_l);
+                v.y = pack2<kBf16>(__uint_as_float(o[g * 8 + 2]) * inv_l, __uint_as_float(o[g * 8 + 3]) * inv_l);
+                v.z = pack2<kBf16>(__uint_as_float(o[g * 8 + 4]) * inv_l, __uint_as_float(o[g * 8 + 5]) * inv_l);
+                v.w = pack2<kBf16>(__uint_as_float(o[g * 8 + 6]) * inv_l, __uint_as_float(o[g * 8 + 7]) * inv_l);
+                const int chunk = c * 4 + g;  // 16-byte chunk index within the row
+                *reinterpret_cast<uint4*>(sO + tid * (D * 2) + ((chunk ^ (tid & 7)) * 16)) = v;
+            }
+        }
+        if (row < sq_b) lse_row[row] = (l_run > 0.f) ? (m_run * p.scale + logf(l_run)) : 0.f;
+        tc_fence_before();
+        named_bar_sync(1, kBlockM);
+        constexpr int kChunksPerRow = D / 8;
+        uint16_t* o_base = reinterpret_cast<uint16_t*>(p.o);
+#pragma unroll 4
+        for (int idx = tid; idx < kBlockM * kChunksPerRow; idx += kBlockM) {
+            const int r = idx / kChunksPerRow, ch = idx % kChunksPerRow;
+            if (m0 + r < sq_b) {
+                const uint4 v = *reinterpret_cast<const uint4*>(sO + r * (D * 2) + ((ch ^ (r & 7)) * 16));
+                *(reinterpret_cast<uint4*>(o_base + ((o_row_base + m0 + r) * p.h + bidh) * D) + ch) = v;
+            }
+        }
+    }
+
+    __syncthreads();
+    if (warp == 4) {
+        __syncwarp();
+        tc_fence_after();
+        tmem_dealloc<512>(tmem_base);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host launcher
+// ------------------------------------------------------------------------------------------------
+template <int D, bool kBf16>
+static int launch_fwd_g(const fa_fwd_params* p, const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv,
+                        const FwdParams& kp, cudaStream_t stream) {
+    using L = FwdSmemG<D>;
+    auto kern = flash_fwd_kernel_sm100_g<D, kBf16>;
+    static bool attr_set = false;  // benign race: idempotent
+    if (!attr_set) {
+        FA_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kBytes));
+        attr_set = true;
+    }
+    dim3 grid((unsigned)((p->seqlen_q + kBlockM - 1) / kBlockM), (unsigned)p->h, (unsigned)p->b);
+    kern<<<grid, 192, L::kBytes, stream>>>(tq, tk, tv, kp);
+    FA_CUDA_CHECK(cudaGetLastError());
+    count_launch();
+    return FA_OK;
+}
+
+int launch_fwd_sm100(const fa_fwd_params* p, cudaStream_t stream) {
+    const bool varlen = p->cu_seqlens_q != nullptr;
+    const bool bf16 = p->dtype == FA_DTYPE_BF16;
+    const uint64_t D = (uint64_t)p->d;
+    if (p->b == 0 || p->seqlen_q == 0 || p->h == 0) return FA_OK;
+    if (varlen ? (p->total_q == 0) : false) return FA_OK;
+
+    FwdParams kp;
+    kp.o = p->o; kp.lse = p->lse; kp.cu_q = p->cu_seqlens_q; kp.cu_k = p->cu_seqlens_k;
+    kp.b = (int)p->b; kp.sq = (int)p->seqlen_q; kp.sk = (int)p->seqlen_k; kp.h = (int)p->h; kp.h_k = (int)p->h_k;
+    kp.hratio = (int)(p->h / p->h_k);
+    kp.is_causal = p->is_causal;
+    kp.scale = 1.0f / sqrtf((float)p->d);
+    kp.scale_log2 = kp.scale * 1.4426950408889634f;
+
+    // TMA views: [batch][row][head][d]; packed varlen tensors are one "batch" of total rows.
+    const uint64_t rows_q = varlen ? (uint64_t)p->total_q : (uint64_t)p->seqlen_q;
+    const uint64_t rows_k = varlen ? (uint64_t)p->total_k : (uint64_t)p->seqlen_k;
+    const uint64_t nb = varlen ? 1 : (uint64_t)p->b;
+    CUtensorMap tq, tk, tv;
+    const uint32_t box[4] = {64, 1, (uint32_t)kBlockM, 1};
+    {
+        const uint64_t dims[4] = {D, (uint64_t)p->h, rows_q, nb};
+        const uint64_t str[3] = {D * 2, (uint64_t)p->h * D * 2, rows_q * (uint64_t)p->h * D * 2};
+        int rc = encode_tmap_4d(&tq, p->q, bf16, dims, str, box);
+        if (rc != FA_OK) return rc;
+    }
+    if (rows_k > 0) {
+        const uint64_t dims[4] = {D, (uint64_t)p->h_k, rows_k, nb};
+        const uint64_t str[3] = {D * 2, (uint64_t)p->h_k * D * 2, rows_k * (uint64_t)p->h_k * D * 2};
+        int rc = encode_tmap_4d(&tk, p->k, bf16, dims, str, box);
+        if (rc != FA_OK) return rc;
+        rc = encode_tmap_4d(&tv, p->v, bf16, dims, str, box);
+        if (rc != FA_OK) return rc;
+    } else {
+        tk = tq; tv = tq;  // never dereferenced: every tile has n_blocks == 0
+    }
+    if (p->d == 128) return bf16 ? launch_fwd_g<128, true>(p, tq, tk, tv, kp, stream) : launch_fwd_g<128, false>(p, tq, tk, tv, kp, stream);
+    if (p->d == 64) return bf16 ? launch_fwd_g<64, true>(p, tq, tk, tv, kp, stream) : launch_fwd_g<64, false>(p, tq, tk, tv, kp, stream);
+    set_error("head_dim %lld not supported (64 or 128)", (long long)p->d);
+    return FA_ERR_INVALID_ARG;
+}
+
+}  // namespace fa100
