@@ -16,6 +16,8 @@
 //
 // This file holds the general kernel "flash_fwd_kernel_sm100_g": one 128-row Q tile per CTA, any
 // sequence lengths, causal, GQA, varlen, d in {64,128}, fp16/bf16.
+#include <stdlib.h>
+
 #include "fa_common.h"
 #include "sm100_ptx.cuh"
 
@@ -307,6 +309,348 @@ flash_fwd_kernel_sm100_g(const __grid_constant__ CUtensorMap tmQ, const __grid_c
     }
 }
 
+// =================================================================================================
+// flash_fwd_kernel_sm100 — the warp-specialised forward.
+//
+// One CTA owns TWO 128-row query tiles of one (batch, head) and walks the key/value tiles once for both:
+//
+//   warpgroup 0 (warps 0-3)  : softmax + output epilogue for query tile 0   (one thread per row)
+//   warpgroup 1 (warps 4-7)  : softmax + output epilogue for query tile 1
+//   warp 8                   : tcgen05.mma issuer (one elected thread)
+//   warp 9                   : TMA producer (Q tiles, then the K/V ring)
+//   warps 10-11              : idle (they only donate registers via setmaxnreg)
+//
+// TMEM (512 columns): S0 [0,128)  S1 [128,256)  O0 [256,256+D)  O1 [384,384+D).  P_t overwrites the first
+// 64 columns of S_t (two 16-bit values per column) and is consumed from there as the A operand of P V.
+// The tensor pipe executes MMAs in issue order, and the issue order is
+//     S0_0 S1_0 | PV0_0 S0_1 PV1_0 S1_1 | PV0_1 S0_2 PV1_1 S1_2 | ...
+// so while warpgroup t runs the softmax of S_t the tensor cores work on the other tile, and "S_t_{j+1} is
+// complete" implies "P V_t_j is complete": the softmax thread may then overwrite P_t and (rarely) rescale
+// O_t without any further synchronisation.
+//
+// Online softmax with lazy rescaling: the running reference max m_ref of a row only moves when the new tile
+// max exceeds it by more than 8 in the log2 domain (P <= 2^8 stays exact enough in fp32 accumulators and in
+// 16-bit P); O_t is rescaled in TMEM only on those steps.  The final O / l and LSE = m_ref*scale + ln l are
+// unchanged by this (the reference rescales on every tile, flash_fwd_kernel.h:675-679).
+// =================================================================================================
+template <int D> struct FwdSmem {
+    static constexpr int kSlab = kBlockM * 128;      // 64-column slab of a 128-row tile: 16 KB
+    static constexpr int kTile = kBlockM * D * 2;    // one 128 x D tile
+    static constexpr int kKvStages = (D == 128) ? 4 : 6;
+    static constexpr int kOffQ = 0;                  // 2 tiles
+    static constexpr int kOffKV = 2 * kTile;         // ring of K/V tiles: K_j -> slot 2j, V_j -> slot 2j+1
+    static constexpr int kOffBar = kOffKV + kKvStages * kTile;
+    static constexpr int kBytes = kOffBar + 512 + 1024;
+};
+constexpr uint32_t kTmemS0 = 0, kTmemO0 = 256;      // tile t: S at kTmemS0 + 128 t, O at kTmemO0 + 128 t
+constexpr float kRescaleThreshold = 8.0f;
+
+template <int D, bool kBf16>
+__global__ void __launch_bounds__(384, 1)
+flash_fwd_kernel_sm100(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                       const __grid_constant__ CUtensorMap tmV, const FwdParams p) {
+    using L = FwdSmem<D>;
+    constexpr int kSlabs = D / 64;
+    constexpr int kStages = L::kKvStages;
+
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5;
+    const int lane = tid & 31;
+    const int wg = warp >> 2;
+    // heavier (later) causal row blocks first
+    const int mblk = p.is_causal ? (gridDim.x - 1 - blockIdx.x) : blockIdx.x;
+    const int m0 = mblk * (2 * kBlockM);
+    const int bidh = blockIdx.y;
+    const int bidb = blockIdx.z;
+    const int bidh_k = bidh / p.hratio;
+
+    int q_row0, k_row0, sq_b, sk_b, tma_b;
+    if (p.cu_q != nullptr) {
+        q_row0 = p.cu_q[bidb];
+        sq_b = p.cu_q[bidb + 1] - q_row0;
+        k_row0 = p.cu_k[bidb];
+        sk_b = p.cu_k[bidb + 1] - k_row0;
+        tma_b = 0;
+    } else {
+        q_row0 = 0; k_row0 = 0; sq_b = p.sq; sk_b = p.sk; tma_b = bidb;
+    }
+    if (m0 >= sq_b) return;
+    const int causal_off = sk_b - sq_b;
+    // key tiles needed by each query tile (0 if the tile has no rows or sees no key)
+    int nblk[2];
+#pragma unroll
+    for (int t = 0; t < 2; ++t) {
+        const int mt = m0 + t * kBlockM;
+        int kv_end = (mt < sq_b) ? sk_b : 0;
+        if (p.is_causal) kv_end = min(kv_end, max(0, mt + kBlockM + causal_off));
+        nblk[t] = (kv_end + kBlockN - 1) / kBlockN;
+    }
+    const int n_blocks = max(nblk[0], nblk[1]);
+    const int64_t o_row_base = (p.cu_q != nullptr) ? (int64_t)q_row0 : (int64_t)bidb * p.sq;
+    float* lse_row = p.lse + ((int64_t)bidb * p.h + bidh) * p.sq;
+
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* sQ = smem + L::kOffQ;
+    uint8_t* sKV = smem + L::kOffKV;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::kOffBar);
+    uint64_t* bar_q = bars;                     // [2]
+    uint64_t* bar_kv_full = bars + 2;           // [kStages]
+    uint64_t* bar_kv_empty = bars + 2 + kStages;
+    uint64_t* bar_s_full = bars + 2 + 2 * kStages;   // [2]
+    uint64_t* bar_p_full = bar_s_full + 2;           // [2]
+    uint64_t* bar_o_full = bar_p_full + 2;           // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_o_full + 2);
+
+    if (warp == 8) {
+        if (lane == 0) {
+            mbar_init(&bar_q[0], 1); mbar_init(&bar_q[1], 1);
+            for (int i = 0; i < kStages; ++i) { mbar_init(&bar_kv_full[i], 1); mbar_init(&bar_kv_empty[i], 1); }
+            for (int t = 0; t < 2; ++t) {
+                mbar_init(&bar_s_full[t], 1);
+                mbar_init(&bar_p_full[t], kBlockM);
+                mbar_init(&bar_o_full[t], 1);
+            }
+            fence_barrier_init();
+        }
+        __syncwarp();
+        tmem_alloc<512>(tmem_slot);
+        tmem_relinquish();
+    } else if (warp == 9 && lane == 0) {
+        tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (wg == 2) {
+        setmaxnreg_dec<56>();
+        if (warp == 9) {
+            // ===================== TMA producer =====================
+            if (lane == 0 && n_blocks > 0) {
+                auto load_kv = [&](const CUtensorMap* tm, int i, int j) {
+                    const int slot = i % kStages;
+                    mbar_wait(&bar_kv_empty[slot], ((i / kStages) & 1) ^ 1);
+                    mbar_arrive_expect_tx(&bar_kv_full[slot], L::kTile);
+                    for (int s = 0; s < kSlabs; ++s)
+                        tma_load_4d(sKV + slot * L::kTile + s * L::kSlab, tm, &bar_kv_full[slot], s * 64, bidh_k,
+                                    k_row0 + j * kBlockN, tma_b);
+                };
+                auto load_q = [&](int t) {
+                    mbar_arrive_expect_tx(&bar_q[t], L::kTile);
+                    for (int s = 0; s < kSlabs; ++s)
+                        tma_load_4d(sQ + t * L::kTile + s * L::kSlab, &tmQ, &bar_q[t], s * 64, bidh,
+                                    q_row0 + m0 + t * kBlockM, tma_b);
+                };
+                if (nblk[0] > 0) load_q(0);
+                load_kv(&tmK, 0, 0);
+                if (nblk[1] > 0) load_q(1);
+                load_kv(&tmV, 1, 0);
+                for (int j = 1; j < n_blocks; ++j) {
+                    load_kv(&tmK, 2 * j, j);
+                    load_kv(&tmV, 2 * j + 1, j);
+                }
+            }
+        } else if (warp == 8) {
+            // ===================== MMA issuer =====================
+            if (lane == 0 && n_blocks > 0) {
+                constexpr uint32_t idesc_s = make_idesc(kBf16, kBlockM, kBlockN, false, false);
+                constexpr uint32_t idesc_pv = make_idesc(kBf16, kBlockM, D, false, true);
+                const uint32_t q_addr = smem_u32(sQ);
+                const uint32_t kv_addr = smem_u32(sKV);
+                auto issue_s = [&](int t, int j) {  // S_t = Q_t K_j^T
+                    const uint32_t qa = q_addr + t * L::kTile;
+                    const uint32_t ka = kv_addr + ((2 * j) % kStages) * L::kTile;
+#pragma unroll
+                    for (int kk = 0; kk < D / 16; ++kk) {
+                        const uint32_t off = (kk >> 2) * L::kSlab + (kk & 3) * 32;
+                        umma_ss(tmem_base + kTmemS0 + t * 128, make_smem_desc(qa + off, 16, 1024),
+                                make_smem_desc(ka + off, 16, 1024), idesc_s, kk > 0);
+                    }
+                    tc_commit(&bar_s_full[t]);
+                };
+                auto issue_pv = [&](int t, int j) {  // O_t += P_t V_j
+                    const uint32_t va = kv_addr + ((2 * j + 1) % kStages) * L::kTile;
+#pragma unroll
+                    for (int kk = 0; kk < kBlockN / 16; ++kk) {
+                        umma_ts(tmem_base + kTmemO0 + t * 128, tmem_base + kTmemS0 + t * 128 + kk * 8,
+                                make_smem_desc(va + kk * 2048, L::kSlab, 1024), idesc_pv, (j > 0 || kk > 0));
+                    }
+                };
+                auto wait_kv = [&](int i) { mbar_wait(&bar_kv_full[i % kStages], (i / kStages) & 1); };
+
+                wait_kv(0);
+                tc_fence_after();
+#pragma unroll
+                for (int t = 0; t < 2; ++t) {
+                    if (nblk[t] > 0) {
+                        mbar_wait(&bar_q[t], 0);
+                        issue_s(t, 0);
+                    }
+                }
+                tc_commit(&bar_kv_empty[0]);
+                for (int j = 0; j < n_blocks; ++j) {
+                    wait_kv(2 * j + 1);  // V_j
+                    bool k_ready = false;
+#pragma unroll
+                    for (int t = 0; t < 2; ++t) {
+                        if (j < nblk[t]) {
+                            mbar_wait(&bar_p_full[t], j & 1);
+                            tc_fence_after();
+                            issue_pv(t, j);
+                            if (j + 1 < nblk[t]) {
+                                if (!k_ready) { wait_kv(2 * j + 2); tc_fence_after(); k_ready = true; }
+                                issue_s(t, j + 1);
+                            } else {
+                                tc_commit(&bar_o_full[t]);
+                            }
+                        }
+                    }
+                    tc_commit(&bar_kv_empty[(2 * j + 1) % kStages]);
+                    if (j + 1 < n_blocks) tc_commit(&bar_kv_empty[(2 * j + 2) % kStages]);
+                }
+            }
+        }
+    } else {
+        // ===================== softmax warpgroups =====================
+        setmaxnreg_inc<224>();
+        const int t = wg;                     // query tile handled by this warpgroup
+        const int r_in_tile = tid & 127;
+        const int mt = m0 + t * kBlockM;
+        const int row = mt + r_in_tile;
+        const int n_t = nblk[t];
+        const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+        const uint32_t tS = tmem_base + lane_base + kTmemS0 + t * 128;
+        const uint32_t tO = tmem_base + lane_base + kTmemO0 + t * 128;
+        uint16_t* o_base = reinterpret_cast<uint16_t*>(p.o);
+        constexpr int kChunksPerRow = D / 8;
+
+        if (n_t == 0) {
+            // no visible key for any row of this tile: O = 0, LSE = 0 (rows beyond seqlen_q are skipped)
+            if (mt < sq_b) {
+                for (int idx = r_in_tile; idx < kBlockM * kChunksPerRow; idx += kBlockM) {
+                    const int r = idx / kChunksPerRow, ch = idx % kChunksPerRow;
+                    if (mt + r < sq_b)
+                        *(reinterpret_cast<uint4*>(o_base + ((o_row_base + mt + r) * p.h + bidh) * D) + ch) = make_uint4(0, 0, 0, 0);
+                }
+                if (row < sq_b) lse_row[row] = 0.f;
+            }
+        } else {
+            int col_limit = sk_b - 1;
+            if (p.is_causal) col_limit = min(col_limit, row + causal_off);
+            float m_ref = -INFINITY, l_run = 0.f;
+            const float c2 = p.scale_log2;
+
+            for (int j = 0; j < n_t; ++j) {
+                const int n0 = j * kBlockN;
+                mbar_wait(&bar_s_full[t], j & 1);
+                tc_fence_after();
+                float s[kBlockN];
+#pragma unroll
+                for (int c = 0; c < kBlockN / 32; ++c)
+                    tmem_ld32(tS + c * 32, *reinterpret_cast<uint32_t(*)[32]>(&s[c * 32]));
+                tmem_wait_ld();
+
+                const bool need_mask = (n0 + kBlockN > sk_b) || (p.is_causal && (n0 + kBlockN - 1 > mt + causal_off));
+                if (need_mask) {
+                    const int lim = col_limit - n0;
+#pragma unroll
+                    for (int c = 0; c < kBlockN; ++c)
+                        if (c > lim) s[c] = -INFINITY;
+                }
+                float mx0 = fmaxf(s[0], s[1]), mx1 = fmaxf(s[2], s[3]);
+#pragma unroll
+                for (int c = 4; c < kBlockN; c += 4) {
+                    mx0 = fmaxf(mx0, fmaxf(s[c], s[c + 1]));
+                    mx1 = fmaxf(mx1, fmaxf(s[c + 2], s[c + 3]));
+                }
+                const float mx = fmaxf(mx0, mx1);
+                if (j == 0) {
+                    m_ref = mx;
+                } else {
+                    // lazy rescale: only when the max moved by more than 2^8
+                    const bool need = (mx - m_ref) * c2 > kRescaleThreshold;
+                    if (__any_sync(0xffffffffu, need)) {
+                        float alpha = 1.f;
+                        if (need) {
+                            alpha = fast_exp2((m_ref - mx) * c2);
+                            m_ref = mx;
+                            l_run *= alpha;
+                        }
+#pragma unroll
+                        for (int c = 0; c < D / 32; ++c) {
+                            uint32_t o[32];
+                            tmem_ld32(tO + c * 32, o);
+                            tmem_wait_ld();
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+                            tmem_st32(tO + c * 32, o);
+                        }
+                    }
+                }
+                const float neg = (m_ref == -INFINITY) ? 0.f : -m_ref * c2;
+                float sum0 = 0.f, sum1 = 0.f;
+                uint32_t pk[kBlockN / 2];
+#pragma unroll
+                for (int c = 0; c < kBlockN; c += 2) {
+                    const float p0 = fast_exp2(fmaf(s[c], c2, neg));
+                    const float p1 = fast_exp2(fmaf(s[c + 1], c2, neg));
+                    sum0 += p0;
+                    sum1 += p1;
+                    pk[c / 2] = pack2<kBf16>(p0, p1);
+                }
+                l_run += sum0 + sum1;
+                tmem_st32(tS, *reinterpret_cast<uint32_t(*)[32]>(&pk[0]));
+                tmem_st32(tS + 32, *reinterpret_cast<uint32_t(*)[32]>(&pk[32]));
+                tmem_wait_st();
+                tc_fence_before();
+                mbar_arrive(&bar_p_full[t]);
+            }
+
+            // ---- epilogue for tile t ----
+            mbar_wait(&bar_o_full[t], 0);
+            tc_fence_after();
+            const float inv_l = (l_run > 0.f) ? (1.f / l_run) : 0.f;
+            uint8_t* sO = sQ + t * L::kTile;   // Q_t is dead: every S_t MMA retired before o_full[t]
+#pragma unroll
+            for (int c = 0; c < D / 32; ++c) {
+                uint32_t o[32];
+                tmem_ld32(tO + c * 32, o);
+                tmem_wait_ld();
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                    uint4 v;
+                    v.x = pack2<kBf16>(__uint_as_float(o[g * 8 + 0]) * inv_l, __uint_as_float(o[g * 8 + 1]) * inv_l);
+                    v.y = pack2<kBf16>(__uint_as_float(o[g * 8 + 2]) * inv_l, __uint_as_float(o[g * 8 + 3]) * inv_l);
+                    v.z = pack2<kBf16>(__uint_as_float(o[g * 8 + 4]) * inv_l, __uint_as_float(o[g * 8 + 5]) * inv_l);
+                    v.w = pack2<kBf16>(__uint_as_float(o[g * 8 + 6]) * inv_l, __uint_as_float(o[g * 8 + 7]) * inv_l);
+                    const int chunk = c * 4 + g;
+                    *reinterpret_cast<uint4*>(sO + r_in_tile * (D * 2) + ((chunk ^ (r_in_tile & 7)) * 16)) = v;
+                }
+            }
+            if (row < sq_b) lse_row[row] = (l_run > 0.f) ? (m_ref * p.scale + logf(l_run)) : 0.f;
+            tc_fence_before();
+            named_bar_sync(1 + t, kBlockM);
+#pragma unroll 4
+            for (int idx = r_in_tile; idx < kBlockM * kChunksPerRow; idx += kBlockM) {
+                const int r = idx / kChunksPerRow, ch = idx % kChunksPerRow;
+                if (mt + r < sq_b) {
+                    const uint4 v = *reinterpret_cast<const uint4*>(sO + r * (D * 2) + ((ch ^ (r & 7)) * 16));
+                    *(reinterpret_cast<uint4*>(o_base + ((o_row_base + mt + r) * p.h + bidh) * D) + ch) = v;
+                }
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 8) {
+        tc_fence_after();
+        tmem_dealloc<512>(tmem_base);
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // host launcher
 // ------------------------------------------------------------------------------------------------
@@ -325,6 +669,33 @@ static int launch_fwd_g(const fa_fwd_params* p, const CUtensorMap& tq, const CUt
     FA_CUDA_CHECK(cudaGetLastError());
     count_launch();
     return FA_OK;
+}
+
+template <int D, bool kBf16>
+static int launch_fwd_ws(const fa_fwd_params* p, const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv,
+                         const FwdParams& kp, cudaStream_t stream) {
+    using L = FwdSmem<D>;
+    auto kern = flash_fwd_kernel_sm100<D, kBf16>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        FA_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kBytes));
+        attr_set = true;
+    }
+    dim3 grid((unsigned)((p->seqlen_q + 2 * kBlockM - 1) / (2 * kBlockM)), (unsigned)p->h, (unsigned)p->b);
+    kern<<<grid, 384, L::kBytes, stream>>>(tq, tk, tv, kp);
+    FA_CUDA_CHECK(cudaGetLastError());
+    count_launch();
+    return FA_OK;
+}
+
+static int fwd_variant() {
+    // FA_B200_FWD=g selects the single-tile bring-up kernel (debug aid); default is the warp-specialised kernel
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("FA_B200_FWD");
+        v = (e && e[0] == 'g') ? 1 : 0;
+    }
+    return v;
 }
 
 int launch_fwd_sm100(const fa_fwd_params* p, cudaStream_t stream) {
@@ -364,8 +735,12 @@ int launch_fwd_sm100(const fa_fwd_params* p, cudaStream_t stream) {
     } else {
         tk = tq; tv = tq;  // never dereferenced: every tile has n_blocks == 0
     }
-    if (p->d == 128) return bf16 ? launch_fwd_g<128, true>(p, tq, tk, tv, kp, stream) : launch_fwd_g<128, false>(p, tq, tk, tv, kp, stream);
-    if (p->d == 64) return bf16 ? launch_fwd_g<64, true>(p, tq, tk, tv, kp, stream) : launch_fwd_g<64, false>(p, tq, tk, tv, kp, stream);
+    if (fwd_variant() == 1) {
+        if (p->d == 128) return bf16 ? launch_fwd_g<128, true>(p, tq, tk, tv, kp, stream) : launch_fwd_g<128, false>(p, tq, tk, tv, kp, stream);
+        if (p->d == 64) return bf16 ? launch_fwd_g<64, true>(p, tq, tk, tv, kp, stream) : launch_fwd_g<64, false>(p, tq, tk, tv, kp, stream);
+    }
+    if (p->d == 128) return bf16 ? launch_fwd_ws<128, true>(p, tq, tk, tv, kp, stream) : launch_fwd_ws<128, false>(p, tq, tk, tv, kp, stream);
+    if (p->d == 64) return bf16 ? launch_fwd_ws<64, true>(p, tq, tk, tv, kp, stream) : launch_fwd_ws<64, false>(p, tq, tk, tv, kp, stream);
     set_error("head_dim %lld not supported (64 or 128)", (long long)p->d);
     return FA_ERR_INVALID_ARG;
 }
