@@ -1,0 +1,141 @@
+"""GPU tests of the reference-facing Python surface: `from flash_attn_turing import fwd, bwd, varlen_fwd, varlen_bwd`
+(+ flash_attn_func), same call shapes as /root/reference/test_flash_attn.py:378-381,756-780."""
+import importlib.util
+import os
+import sys
+
+import pytest
+import torch
+
+from gpu_ref import assert_close, attention_ref
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def fat():
+    import flash_attn_turing
+    return flash_attn_turing
+
+
+def _rand(b, sq, sk, h, hk, d, dt, seed=0):
+    torch.manual_seed(seed)
+    return (torch.randn(b, sq, h, d, device="cuda", dtype=dt), torch.randn(b, sk, hk, d, device="cuda", dtype=dt),
+            torch.randn(b, sk, hk, d, device="cuda", dtype=dt), torch.randn(b, sq, h, d, device="cuda", dtype=dt))
+
+
+@pytest.mark.parametrize("dt", [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("causal", [False, True])
+def test_fwd_bwd_like_the_reference_test(fat, dt, causal):
+    q, k, v, do = _rand(3, 129, 257, 6, 3, 128, dt)
+    o, l = fat.fwd(q, k, v, causal)
+    dq, dk, dv = fat.bwd(q, k, v, o, l, do, causal)
+    assert o.dtype == dt and o.shape == q.shape and l.dtype == torch.float32 and l.shape == (3, 6, 129)
+    assert dq.shape == q.shape and dk.shape == k.shape and dv.shape == v.shape
+    ref = attention_ref(q, k, v, causal, do)
+    for name, x, r in zip(("o", "dq", "dk", "dv"), (o, dq, dk, dv), (ref[0], ref[2], ref[3], ref[4])):
+        assert_close(x, r, dt, name)
+
+
+def test_varlen_surface(fat):
+    dt = torch.float16
+    lens_q, lens_k = [5, 128, 77], [130, 3, 77]
+    cu_q = torch.tensor([0, 5, 133, 210], dtype=torch.int32, device="cuda")
+    cu_k = torch.tensor([0, 130, 133, 210], dtype=torch.int32, device="cuda")
+    torch.manual_seed(5)
+    q = torch.randn(210, 4, 64, device="cuda", dtype=dt)
+    k = torch.randn(210, 2, 64, device="cuda", dtype=dt)
+    v = torch.randn(210, 2, 64, device="cuda", dtype=dt)
+    do = torch.randn_like(q)
+    out, l = fat.varlen_fwd(q, k, v, cu_q, cu_k, 128, 130, True)
+    dq, dk, dv = fat.varlen_bwd(q, k, v, out, l, do, cu_q, cu_k, 128, 130, True)
+    assert l.shape == (3, 4, 128)
+    for i in range(3):
+        qs, qe, ks, ke = int(cu_q[i]), int(cu_q[i + 1]), int(cu_k[i]), int(cu_k[i + 1])
+        ref = attention_ref(q[qs:qe][None], k[ks:ke][None], v[ks:ke][None], True, do[qs:qe][None])
+        assert_close(out[qs:qe][None], ref[0], dt, "out")
+        assert_close(dq[qs:qe][None], ref[2], dt, "dq")
+        assert_close(dk[ks:ke][None], ref[3], dt, "dk")
+        assert_close(dv[ks:ke][None], ref[4], dt, "dv")
+
+
+def test_flash_attn_func_autograd(fat):
+    dt = torch.bfloat16
+    q, k, v, do = _rand(2, 256, 256, 4, 4, 128, dt, seed=9)
+    q.requires_grad_(True); k.requires_grad_(True); v.requires_grad_(True)
+    # README signature: flash_attn_func(q, k, v, batch_size, seq_len, num_heads, head_dim)
+    out = fat.flash_attn_func(q, k, v, 2, 256, 4, 128)
+    out.backward(do)
+    ref = attention_ref(q.detach(), k.detach(), v.detach(), False, do)
+    assert_close(out.detach(), ref[0], dt, "out")
+    assert_close(q.grad, ref[2], dt, "dq")
+    assert_close(k.grad, ref[3], dt, "dk")
+    assert_close(v.grad, ref[4], dt, "dv")
+    out_c = fat.flash_attn_func(q.detach(), k.detach(), v.detach(), causal=True)
+    assert_close(out_c, attention_ref(q.detach(), k.detach(), v.detach(), True)[0], dt, "out causal")
+
+
+def test_error_behaviour_matches_reference_checks(fat):
+    q, k, v, _ = _rand(1, 64, 64, 4, 2, 128, torch.float16)
+    with pytest.raises(RuntimeError, match="rank-4"):
+        fat.fwd(q[0], k, v, False)
+    with pytest.raises(RuntimeError, match="divisible"):
+        fat.fwd(q, k[:, :, :1].repeat(1, 1, 3, 1).contiguous(), v[:, :, :1].repeat(1, 1, 3, 1).contiguous(), False)
+    with pytest.raises(RuntimeError, match="head_dim"):
+        fat.fwd(q[..., :96].contiguous(), k[..., :96].contiguous(), v[..., :96].contiguous(), False)
+    with pytest.raises(RuntimeError, match="float16 or bfloat16|same dtype"):
+        fat.fwd(q.float(), k.float(), v.float(), False)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        fat.fwd(q.cpu(), k.cpu(), v.cpu(), False)
+    with pytest.raises(RuntimeError, match="contiguous"):
+        fat.fwd(q.transpose(1, 2), k, v, False)
+    cu = torch.tensor([0, 64], dtype=torch.int64, device="cuda")
+    with pytest.raises(RuntimeError, match="int32"):
+        fat.varlen_fwd(q[0], k[0], v[0], cu, cu, 64, 64, False)
+
+
+def test_non_default_stream_and_launch_count(fat):
+    q, k, v, _ = _rand(1, 512, 512, 2, 2, 128, torch.bfloat16)
+    o0, l0 = fat.fwd(q, k, v, True)
+    st = torch.cuda.Stream()
+    st.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(st):
+        o1, l1 = fat.fwd(q, k, v, True)
+    st.synchronize()
+    assert torch.equal(o0, o1) and torch.equal(l0, l1)
+    assert fat.last_launch_count() == 1
+
+
+def test_cuda_graph_capture(fat):
+    """the operator is capturable: no host sync, no per-call allocation outside torch's caching allocator"""
+    q, k, v, _ = _rand(2, 1024, 1024, 4, 4, 128, torch.bfloat16)
+    fat.fwd(q, k, v, False)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        o, l = fat.fwd(q, k, v, False)
+    g.replay()
+    torch.cuda.synchronize()
+    assert_close(o, attention_ref(q, k, v, False)[0], torch.bfloat16, "graph replay")
+
+
+REF_TEST = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "baseline", "_ref", "test_flash_attn.py")
+
+
+@pytest.mark.skipif(not os.path.exists(REF_TEST), reason="baseline/_ref/test_flash_attn.py not staged (baseline/build_ref.sh)")
+def test_reference_own_test_file_sampled(fat):
+    """run the reference's OWN test functions, unmodified, against this module (a 1-in-37 sample of its dense grid and
+    a 1-in-53 sample of its varlen grid; the full 5 088-case run is recorded in profiles/)"""
+    import itertools
+    spec = importlib.util.spec_from_file_location("ref_test_flash_attn", REF_TEST)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    seqs = [(1, 1), (63, 65), (64, 64), (65, 63), (127, 129), (128, 128), (129, 127), (1023, 1025), (1024, 1024), (1025, 1023), (1, 1025), (1025, 1)]
+    grid = list(itertools.product([64, 128], [1, 3], [(2, 1), (4, 2), (6, 3), (6, 1)], [False, True], seqs))
+    for i, (d, b, (h, hk), causal, (sq, sk)) in enumerate(grid):
+        if i % 37 == 0:
+            mod.test_flash_attn_bwd(b, h, hk, sq, sk, d, causal, torch.float16)
+    torch.manual_seed(11)
+    for i, (d, b, (h, hk), causal, (sq, sk)) in enumerate(grid):
+        if i % 53 == 0:
+            mod.test_flash_attn_bwd_varlen(b, h, hk, sq, sk, d, causal, torch.float16)
