@@ -32,7 +32,19 @@ struct FwdParams {
     int is_causal;
     float scale;       // 1/sqrt(d)
     float scale_log2;  // log2(e)/sqrt(d)
+    float inv_scale_log2;
+    long long* trace;  // FA_TRACE builds only: clock64() stamps of CTA (0,0,0), [role][j][event]
 };
+
+#ifdef FA_TRACE
+#define FA_TRACE_EVENT(role, j, ev)                                                              \
+    do {                                                                                         \
+        if (p.trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && (j) < 64)        \
+            p.trace[((role) * 64 + (j)) * 8 + (ev)] = clock64();                                 \
+    } while (0)
+#else
+#define FA_TRACE_EVENT(role, j, ev) do {} while (0)
+#endif
 
 constexpr int kBlockM = 128;  // query rows per tile  (= TMEM lanes = UMMA M)
 constexpr int kBlockN = 128;  // key rows per tile    (= UMMA N of S, K extent of PV)
@@ -345,7 +357,7 @@ template <int D> struct FwdSmem {
 constexpr uint32_t kTmemS0 = 0, kTmemO0 = 256;      // tile t: S at kTmemS0 + 128 t, O at kTmemO0 + 128 t
 constexpr float kRescaleThreshold = 8.0f;
 
-template <int D, bool kBf16>
+template <int D, bool kBf16, int kEmu>
 __global__ void __launch_bounds__(384, 1)
 flash_fwd_kernel_sm100(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                        const __grid_constant__ CUtensorMap tmV, const FwdParams p) {
@@ -398,8 +410,8 @@ flash_fwd_kernel_sm100(const __grid_constant__ CUtensorMap tmQ, const __grid_con
     uint64_t* bar_kv_full = bars + 2;           // [kStages]
     uint64_t* bar_kv_empty = bars + 2 + kStages;
     uint64_t* bar_s_full = bars + 2 + 2 * kStages;   // [2]
-    uint64_t* bar_p_full = bar_s_full + 2;           // [2]
-    uint64_t* bar_o_full = bar_p_full + 2;           // [2]
+    uint64_t* bar_p_full = bar_s_full + 2;           // [2 tiles][2 halves]: P_t columns [0,64) / [64,128) written
+    uint64_t* bar_o_full = bar_p_full + 4;           // [2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_o_full + 2);
 
     if (warp == 8) {
@@ -408,7 +420,8 @@ flash_fwd_kernel_sm100(const __grid_constant__ CUtensorMap tmQ, const __grid_con
             for (int i = 0; i < kStages; ++i) { mbar_init(&bar_kv_full[i], 1); mbar_init(&bar_kv_empty[i], 1); }
             for (int t = 0; t < 2; ++t) {
                 mbar_init(&bar_s_full[t], 1);
-                mbar_init(&bar_p_full[t], kBlockM);
+                mbar_init(&bar_p_full[2 * t], kBlockM);
+                mbar_init(&bar_p_full[2 * t + 1], kBlockM);
                 mbar_init(&bar_o_full[t], 1);
             }
             fence_barrier_init();
@@ -425,7 +438,7 @@ flash_fwd_kernel_sm100(const __grid_constant__ CUtensorMap tmQ, const __grid_con
     const uint32_t tmem_base = *tmem_slot;
 
     if (wg == 2) {
-        setmaxnreg_dec<56>();
+        setmaxnreg_dec<72>();
         if (warp == 9) {
             // ===================== TMA producer =====================
             if (lane == 0 && n_blocks > 0) {
@@ -454,67 +467,85 @@ flash_fwd_kernel_sm100(const __grid_constant__ CUtensorMap tmQ, const __grid_con
             }
         } else if (warp == 8) {
             // ===================== MMA issuer =====================
-            if (lane == 0 && n_blocks > 0) {
+            // The whole warp walks the (warp-uniform) schedule and waits on the barriers; one elected lane issues
+            // the tcgen05 instructions.  Everything that feeds a descriptor is made provably warp-uniform
+            // (__shfl_sync broadcast) so the compiler keeps it in uniform registers instead of emitting a
+            // per-MMA "waterfall" loop — the issue rate of this warp bounds the whole kernel.
+            const int nb0 = __shfl_sync(0xffffffffu, nblk[0], 0);
+            const int nb1 = __shfl_sync(0xffffffffu, nblk[1], 0);
+            const int nbmax = max(nb0, nb1);
+            if (nbmax > 0) {
+                const bool leader = elect_one();
                 constexpr uint32_t idesc_s = make_idesc(kBf16, kBlockM, kBlockN, false, false);
                 constexpr uint32_t idesc_pv = make_idesc(kBf16, kBlockM, D, false, true);
-                const uint32_t q_addr = smem_u32(sQ);
-                const uint32_t kv_addr = smem_u32(sKV);
+                const uint32_t tm = __shfl_sync(0xffffffffu, tmem_base, 0);
+                const uint32_t q_lo = __shfl_sync(0xffffffffu, desc_lo(smem_u32(sQ), 16), 0);
+                const uint32_t kv_lo = __shfl_sync(0xffffffffu, desc_lo(smem_u32(sKV), 16), 0);
+                const uint32_t v_lo = __shfl_sync(0xffffffffu, desc_lo(smem_u32(sKV), L::kSlab), 0);
+                constexpr uint32_t kTile16 = L::kTile >> 4;   // descriptor address units are 16 bytes
                 auto issue_s = [&](int t, int j) {  // S_t = Q_t K_j^T
-                    const uint32_t qa = q_addr + t * L::kTile;
-                    const uint32_t ka = kv_addr + ((2 * j) % kStages) * L::kTile;
+                    if (leader) {
+                        const uint32_t qa = q_lo + t * kTile16;
+                        const uint32_t ka = kv_lo + ((2 * j) % kStages) * kTile16;
 #pragma unroll
-                    for (int kk = 0; kk < D / 16; ++kk) {
-                        const uint32_t off = (kk >> 2) * L::kSlab + (kk & 3) * 32;
-                        umma_ss(tmem_base + kTmemS0 + t * 128, make_smem_desc(qa + off, 16, 1024),
-                                make_smem_desc(ka + off, 16, 1024), idesc_s, kk > 0);
+                        for (int kk = 0; kk < D / 16; ++kk) {
+                            const uint32_t off = ((kk >> 2) * L::kSlab + (kk & 3) * 32) >> 4;
+                            umma_ss(tm + kTmemS0 + t * 128, desc_make(qa + off, kDescHiK), desc_make(ka + off, kDescHiK),
+                                    idesc_s, kk > 0);
+                        }
+                        tc_commit(&bar_s_full[t]);
                     }
-                    tc_commit(&bar_s_full[t]);
                 };
-                auto issue_pv = [&](int t, int j) {  // O_t += P_t V_j
-                    const uint32_t va = kv_addr + ((2 * j + 1) % kStages) * L::kTile;
+                auto issue_pv = [&](int t, int j, int half) {  // O_t += P_t[:, 64 half : 64 half + 64] V_j[64 half ...]
+                    if (leader) {
+                        const uint32_t va = v_lo + ((2 * j + 1) % kStages) * kTile16;
 #pragma unroll
-                    for (int kk = 0; kk < kBlockN / 16; ++kk) {
-                        umma_ts(tmem_base + kTmemO0 + t * 128, tmem_base + kTmemS0 + t * 128 + kk * 8,
-                                make_smem_desc(va + kk * 2048, L::kSlab, 1024), idesc_pv, (j > 0 || kk > 0));
+                        for (int kk = half * 4; kk < half * 4 + 4; ++kk) {
+                            umma_ts(tm + kTmemO0 + t * 128, tm + kTmemS0 + t * 128 + kk * 8,
+                                    desc_make(va + kk * (2048 >> 4), kDescHiK), idesc_pv, (j > 0 || kk > 0));
+                        }
                     }
                 };
                 auto wait_kv = [&](int i) { mbar_wait(&bar_kv_full[i % kStages], (i / kStages) & 1); };
+                auto commit = [&](uint64_t* bar) { if (leader) tc_commit(bar); };
 
                 wait_kv(0);
                 tc_fence_after();
-#pragma unroll
-                for (int t = 0; t < 2; ++t) {
-                    if (nblk[t] > 0) {
-                        mbar_wait(&bar_q[t], 0);
-                        issue_s(t, 0);
-                    }
-                }
-                tc_commit(&bar_kv_empty[0]);
-                for (int j = 0; j < n_blocks; ++j) {
+                if (nb0 > 0) { mbar_wait(&bar_q[0], 0); issue_s(0, 0); }
+                if (nb1 > 0) { mbar_wait(&bar_q[1], 0); issue_s(1, 0); }
+                commit(&bar_kv_empty[0]);
+                for (int j = 0; j < nbmax; ++j) {
                     wait_kv(2 * j + 1);  // V_j
                     bool k_ready = false;
 #pragma unroll
                     for (int t = 0; t < 2; ++t) {
-                        if (j < nblk[t]) {
-                            mbar_wait(&bar_p_full[t], j & 1);
+                        const int nbt = t == 0 ? nb0 : nb1;
+                        if (j < nbt) {
+                            mbar_wait(&bar_p_full[2 * t], j & 1);
                             tc_fence_after();
-                            issue_pv(t, j);
-                            if (j + 1 < nblk[t]) {
+                            if (lane == 0) FA_TRACE_EVENT(2, j, t);
+                            issue_pv(t, j, 0);
+                            mbar_wait(&bar_p_full[2 * t + 1], j & 1);
+                            tc_fence_after();
+                            issue_pv(t, j, 1);
+                            if (j + 1 < nbt) {
                                 if (!k_ready) { wait_kv(2 * j + 2); tc_fence_after(); k_ready = true; }
                                 issue_s(t, j + 1);
                             } else {
-                                tc_commit(&bar_o_full[t]);
+                                commit(&bar_o_full[t]);
                             }
+                            if (lane == 0) FA_TRACE_EVENT(2, j, 2 + t);
                         }
                     }
-                    tc_commit(&bar_kv_empty[(2 * j + 1) % kStages]);
-                    if (j + 1 < n_blocks) tc_commit(&bar_kv_empty[(2 * j + 2) % kStages]);
+                    commit(&bar_kv_empty[(2 * j + 1) % kStages]);
+                    if (j + 1 < nbmax) commit(&bar_kv_empty[(2 * j + 2) % kStages]);
+                    __syncwarp();
                 }
             }
         }
     } else {
         // ===================== softmax warpgroups =====================
-        setmaxnreg_inc<224>();
+        setmaxnreg_inc<216>();
         const int t = wg;                     // query tile handled by this warpgroup
         const int r_in_tile = tid & 127;
         const int mt = m0 + t * kBlockM;
@@ -546,11 +577,13 @@ flash_fwd_kernel_sm100(const __grid_constant__ CUtensorMap tmQ, const __grid_con
                 const int n0 = j * kBlockN;
                 mbar_wait(&bar_s_full[t], j & 1);
                 tc_fence_after();
+                if (r_in_tile == 0) FA_TRACE_EVENT(t, j, 0);
                 float s[kBlockN];
 #pragma unroll
                 for (int c = 0; c < kBlockN / 32; ++c)
                     tmem_ld32(tS + c * 32, *reinterpret_cast<uint32_t(*)[32]>(&s[c * 32]));
                 tmem_wait_ld();
+                if (r_in_tile == 0) FA_TRACE_EVENT(t, j, 1);
 
                 const bool need_mask = (n0 + kBlockN > sk_b) || (p.is_causal && (n0 + kBlockN - 1 > mt + causal_off));
                 if (need_mask) {
@@ -559,13 +592,16 @@ flash_fwd_kernel_sm100(const __grid_constant__ CUtensorMap tmQ, const __grid_con
                     for (int c = 0; c < kBlockN; ++c)
                         if (c > lim) s[c] = -INFINITY;
                 }
-                float mx0 = fmaxf(s[0], s[1]), mx1 = fmaxf(s[2], s[3]);
+                // row max: 4 independent chains of 3-input max (FMNMX3)
+                float mxa = fmaxf(s[0], s[1]), mxb = fmaxf(s[2], s[3]), mxc = fmaxf(s[4], s[5]), mxd = fmaxf(s[6], s[7]);
 #pragma unroll
-                for (int c = 4; c < kBlockN; c += 4) {
-                    mx0 = fmaxf(mx0, fmaxf(s[c], s[c + 1]));
-                    mx1 = fmaxf(mx1, fmaxf(s[c + 2], s[c + 3]));
+                for (int c = 8; c < kBlockN; c += 8) {
+                    mxa = fmaxf(mxa, fmaxf(s[c], s[c + 1]));
+                    mxb = fmaxf(mxb, fmaxf(s[c + 2], s[c + 3]));
+                    mxc = fmaxf(mxc, fmaxf(s[c + 4], s[c + 5]));
+                    mxd = fmaxf(mxd, fmaxf(s[c + 6], s[c + 7]));
                 }
-                const float mx = fmaxf(mx0, mx1);
+                const float mx = fmaxf(fmaxf(mxa, mxb), fmaxf(mxc, mxd));
                 if (j == 0) {
                     m_ref = mx;
                 } else {
@@ -590,28 +626,57 @@ flash_fwd_kernel_sm100(const __grid_constant__ CUtensorMap tmQ, const __grid_con
                     }
                 }
                 const float neg = (m_ref == -INFINITY) ? 0.f : -m_ref * c2;
-                float sum0 = 0.f, sum1 = 0.f;
-                uint32_t pk[kBlockN / 2];
+                if (r_in_tile == 0) FA_TRACE_EVENT(t, j, 2);
+                // P = 2^(s*c2 + neg).  kEmu of every 4 elements are evaluated on the FMA pipe (Cody-Waite split +
+                // degree-3 minimax polynomial, |rel err| < 7.5e-5, far below the 16-bit rounding of P) instead of the
+                // 16-per-clock MUFU.EX2 unit, which otherwise is as loaded as the tensor pipe at d=128.
+                const float s_floor = (-125.f - neg) * p.inv_scale_log2;  // clamp so that 2^x stays a normal float
+                const float2 c2v = make_float2(c2, c2), negv = make_float2(neg, neg);
+                const float2 magic = make_float2(12582912.f, 12582912.f);       // 1.5 * 2^23
+                float2 sum = make_float2(0.f, 0.f);
+                // two neighbouring columns at a time on the packed fp32x2 pipe (FFMA2 / FADD2)
+                auto ex2_pair = [&](float a, float b, bool emulate) -> float2 {
+                    if (!emulate) {
+                        const float2 x = __ffma2_rn(make_float2(a, b), c2v, negv);
+                        return make_float2(fast_exp2(x.x), fast_exp2(x.y));
+                    }
+                    const float2 x = __ffma2_rn(make_float2(fmaxf(a, s_floor), fmaxf(b, s_floor)), c2v, negv);
+                    const float2 tt = __fadd2_rn(x, magic);                   // low mantissa bits = rint(x)
+                    const float2 nnf = __ffma2_rn(tt, make_float2(-1.f, -1.f), magic);   // -rint(x), exact
+                    const float2 f = __fadd2_rn(x, nnf);                      // x - rint(x)  in [-0.5, 0.5]
+                    float2 pl = __ffma2_rn(make_float2(0.05517115816473961f, 0.05517115816473961f), f,
+                                           make_float2(0.2426101416349411f, 0.2426101416349411f));
+                    pl = __ffma2_rn(pl, f, make_float2(0.6932609677314758f, 0.6932609677314758f));
+                    pl = __ffma2_rn(pl, f, make_float2(0.9999281167984009f, 0.9999281167984009f));
+                    return make_float2(__uint_as_float(__float_as_uint(pl.x) + (__float_as_uint(tt.x) << 23)),
+                                       __uint_as_float(__float_as_uint(pl.y) + (__float_as_uint(tt.y) << 23)));
+                };
 #pragma unroll
-                for (int c = 0; c < kBlockN; c += 2) {
-                    const float p0 = fast_exp2(fmaf(s[c], c2, neg));
-                    const float p1 = fast_exp2(fmaf(s[c + 1], c2, neg));
-                    sum0 += p0;
-                    sum1 += p1;
-                    pk[c / 2] = pack2<kBf16>(p0, p1);
+                for (int half = 0; half < 2; ++half) {
+                    uint32_t pk[32];
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) {
+                        const int c = half * 64 + 2 * i;
+                        const float2 pp = ex2_pair(s[c], s[c + 1], (i & 3) < kEmu);
+                        sum = __fadd2_rn(sum, pp);
+                        pk[i] = pack2<kBf16>(pp.x, pp.y);
+                    }
+                    if (half == 1 && r_in_tile == 0) FA_TRACE_EVENT(t, j, 3);
+                    tmem_st32(tS + half * 32, pk);
+                    tmem_wait_st();
+                    tc_fence_before();
+                    mbar_arrive(&bar_p_full[2 * t + half]);
                 }
+                const float sum0 = sum.x, sum1 = sum.y;
                 l_run += sum0 + sum1;
-                tmem_st32(tS, *reinterpret_cast<uint32_t(*)[32]>(&pk[0]));
-                tmem_st32(tS + 32, *reinterpret_cast<uint32_t(*)[32]>(&pk[32]));
-                tmem_wait_st();
-                tc_fence_before();
-                mbar_arrive(&bar_p_full[t]);
+                if (r_in_tile == 0) FA_TRACE_EVENT(t, j, 4);
             }
 
             // ---- epilogue for tile t ----
             mbar_wait(&bar_o_full[t], 0);
             tc_fence_after();
-            const float inv_l = (l_run > 0.f) ? (1.f / l_run) : 0.f;
+            const bool row_empty = (m_ref == -INFINITY) || !(l_run > 0.f);   // no visible key: O = 0, LSE = 0
+            const float inv_l = row_empty ? 0.f : (1.f / l_run);
             uint8_t* sO = sQ + t * L::kTile;   // Q_t is dead: every S_t MMA retired before o_full[t]
 #pragma unroll
             for (int c = 0; c < D / 32; ++c) {
@@ -629,7 +694,7 @@ flash_fwd_kernel_sm100(const __grid_constant__ CUtensorMap tmQ, const __grid_con
                     *reinterpret_cast<uint4*>(sO + r_in_tile * (D * 2) + ((chunk ^ (r_in_tile & 7)) * 16)) = v;
                 }
             }
-            if (row < sq_b) lse_row[row] = (l_run > 0.f) ? (m_ref * p.scale + logf(l_run)) : 0.f;
+            if (row < sq_b) lse_row[row] = row_empty ? 0.f : (m_ref * p.scale + logf(l_run));
             tc_fence_before();
             named_bar_sync(1 + t, kBlockM);
 #pragma unroll 4
@@ -671,11 +736,11 @@ static int launch_fwd_g(const fa_fwd_params* p, const CUtensorMap& tq, const CUt
     return FA_OK;
 }
 
-template <int D, bool kBf16>
+template <int D, bool kBf16, int kEmu>
 static int launch_fwd_ws(const fa_fwd_params* p, const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv,
                          const FwdParams& kp, cudaStream_t stream) {
     using L = FwdSmem<D>;
-    auto kern = flash_fwd_kernel_sm100<D, kBf16>;
+    auto kern = flash_fwd_kernel_sm100<D, kBf16, kEmu>;
     static bool attr_set = false;
     if (!attr_set) {
         FA_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kBytes));
@@ -686,6 +751,17 @@ static int launch_fwd_ws(const fa_fwd_params* p, const CUtensorMap& tq, const CU
     FA_CUDA_CHECK(cudaGetLastError());
     count_launch();
     return FA_OK;
+}
+
+static int fwd_emu() {
+    // FA_B200_EMU=n: n of every 4 exponentials per row are evaluated by polynomial on the FMA pipe (tuning knob)
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("FA_B200_EMU");
+        v = e ? atoi(e) : 0;
+        if (v < 0 || v > 2) v = 0;
+    }
+    return v;
 }
 
 static int fwd_variant() {
@@ -712,6 +788,17 @@ int launch_fwd_sm100(const fa_fwd_params* p, cudaStream_t stream) {
     kp.is_causal = p->is_causal;
     kp.scale = 1.0f / sqrtf((float)p->d);
     kp.scale_log2 = kp.scale * 1.4426950408889634f;
+    kp.inv_scale_log2 = 1.0f / kp.scale_log2;
+    kp.trace = nullptr;
+#ifdef FA_TRACE
+    static long long* d_trace = nullptr;
+    const bool do_trace = getenv("FA_B200_TRACE") != nullptr;
+    if (do_trace) {
+        if (!d_trace) cudaMalloc(&d_trace, 3 * 64 * 8 * sizeof(long long));
+        cudaMemsetAsync(d_trace, 0, 3 * 64 * 8 * sizeof(long long), stream);
+        kp.trace = d_trace;
+    }
+#endif
 
     // TMA views: [batch][row][head][d]; packed varlen tensors are one "batch" of total rows.
     const uint64_t rows_q = varlen ? (uint64_t)p->total_q : (uint64_t)p->seqlen_q;
@@ -739,8 +826,34 @@ int launch_fwd_sm100(const fa_fwd_params* p, cudaStream_t stream) {
         if (p->d == 128) return bf16 ? launch_fwd_g<128, true>(p, tq, tk, tv, kp, stream) : launch_fwd_g<128, false>(p, tq, tk, tv, kp, stream);
         if (p->d == 64) return bf16 ? launch_fwd_g<64, true>(p, tq, tk, tv, kp, stream) : launch_fwd_g<64, false>(p, tq, tk, tv, kp, stream);
     }
-    if (p->d == 128) return bf16 ? launch_fwd_ws<128, true>(p, tq, tk, tv, kp, stream) : launch_fwd_ws<128, false>(p, tq, tk, tv, kp, stream);
-    if (p->d == 64) return bf16 ? launch_fwd_ws<64, true>(p, tq, tk, tv, kp, stream) : launch_fwd_ws<64, false>(p, tq, tk, tv, kp, stream);
+#ifdef FA_TRACE
+    if (do_trace && p->d == 128 && bf16) {
+        int rc = fwd_emu() == 0 ? launch_fwd_ws<128, true, 0>(p, tq, tk, tv, kp, stream)
+               : fwd_emu() == 1 ? launch_fwd_ws<128, true, 1>(p, tq, tk, tv, kp, stream)
+                                : launch_fwd_ws<128, true, 2>(p, tq, tk, tv, kp, stream);
+        cudaStreamSynchronize(stream);
+        static long long h[3 * 64 * 8];
+        cudaMemcpy(h, d_trace, sizeof(h), cudaMemcpyDeviceToHost);
+        const long long t0 = h[0];
+        printf("TRACE role j : events (cycles since first S-full of WG0)\n");
+        for (int r = 0; r < 3; ++r)
+            for (int j = 0; j < 12; ++j) {
+                printf("TRACE %d %2d :", r, j);
+                for (int e = 0; e < 5; ++e) printf(" %8lld", h[(r * 64 + j) * 8 + e] ? h[(r * 64 + j) * 8 + e] - t0 : -1LL);
+                printf("\n");
+            }
+        fflush(stdout);
+        return rc;
+    }
+#endif
+    if (p->d == 128) {
+        switch (fwd_emu()) {
+            case 0: return bf16 ? launch_fwd_ws<128, true, 0>(p, tq, tk, tv, kp, stream) : launch_fwd_ws<128, false, 0>(p, tq, tk, tv, kp, stream);
+            case 1: return bf16 ? launch_fwd_ws<128, true, 1>(p, tq, tk, tv, kp, stream) : launch_fwd_ws<128, false, 1>(p, tq, tk, tv, kp, stream);
+            default: return bf16 ? launch_fwd_ws<128, true, 2>(p, tq, tk, tv, kp, stream) : launch_fwd_ws<128, false, 2>(p, tq, tk, tv, kp, stream);
+        }
+    }
+    if (p->d == 64) return bf16 ? launch_fwd_ws<64, true, 0>(p, tq, tk, tv, kp, stream) : launch_fwd_ws<64, false, 0>(p, tq, tk, tv, kp, stream);
     set_error("head_dim %lld not supported (64 or 128)", (long long)p->d);
     return FA_ERR_INVALID_ARG;
 }

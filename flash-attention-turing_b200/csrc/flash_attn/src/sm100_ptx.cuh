@@ -166,6 +166,15 @@ FA_DEVICE uint64_t make_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32
            (uint64_t((sbo_bytes >> 4) & 0x3FFF) << 32);
 }
 
+// Split form used on the MMA issue path: the low word carries (address >> 4) and the leading-dim offset, the high
+// word (stride offset 1024 B, version, 128B swizzle) is a compile-time constant; stepping a descriptor is then a
+// single 32-bit add on the low word (tile bases are 1024-B aligned and shared memory is < 256 KB, so no carry).
+constexpr uint32_t kDescHiK = uint32_t((kDescSwizzle128 >> 32) | (1024u >> 4));
+FA_DEVICE uint32_t desc_lo(uint32_t smem_addr, uint32_t lbo_bytes) {
+    return ((smem_addr & 0x3FFFF) >> 4) | (((lbo_bytes >> 4) & 0x3FFF) << 16);
+}
+FA_DEVICE uint64_t desc_make(uint32_t lo, uint32_t hi) { return (uint64_t(hi) << 32) | lo; }
+
 // Instruction descriptor for kind::f16 (fp16/bf16 operands, fp32 accumulate):
 //   [4,6) D format (1 = f32)  [7,10) A format  [10,13) B format (0 = f16, 1 = bf16)
 //   [15] A major  [16] B major (0 = K-major, 1 = MN-major)  [17,23) N>>3  [24,29) M>>4

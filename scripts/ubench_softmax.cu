@@ -1,0 +1,97 @@
+// Micro-benchmark (GPU box): cycles per 128-element softmax row-tile for several instruction mixes, with 1 or 2
+// warps resident per SM sub-partition.  Used to choose the softmax design of flash_fwd_kernel_sm100.
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o scripts/ubench_softmax.bin scripts/ubench_softmax.cu
+#include <cstdio>
+#include <cstdint>
+#include <cuda_runtime.h>
+
+__device__ __forceinline__ float ex2f(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) { uint32_t r; asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo)); return r; }
+
+template <int kEmu, int kMode>
+__device__ __forceinline__ void row_tile(float (&s)[128], float c2, float neg, float2& sum, uint32_t (&pk)[64]) {
+    const float2 c2v = make_float2(c2, c2), negv = make_float2(neg, neg);
+    const float2 magic = make_float2(12582912.f, 12582912.f);
+#pragma unroll
+    for (int i = 0; i < 64; ++i) {
+        float2 pp;
+        const bool emulate = (i & 3) < kEmu;
+        if (kMode == 1) {  // scalar math (FFMA/FADD) instead of packed
+            const float x0 = fmaf(s[2 * i], c2, neg), x1 = fmaf(s[2 * i + 1], c2, neg);
+            pp = make_float2(ex2f(x0), ex2f(x1));
+            sum.x += pp.x; sum.y += pp.y;
+            pk[i] = pack_bf16(pp.x, pp.y);
+            continue;
+        }
+        const float2 x = __ffma2_rn(make_float2(s[2 * i], s[2 * i + 1]), c2v, negv);
+        if (!emulate) {
+            pp = make_float2(ex2f(x.x), ex2f(x.y));
+        } else {
+            const float2 tt = __fadd2_rn(x, magic);
+            const float2 nnf = __ffma2_rn(tt, make_float2(-1.f, -1.f), magic);   // -(rint x)
+            const float2 f = __fadd2_rn(x, nnf);
+            float2 pl = __ffma2_rn(make_float2(0.05517115816473961f, 0.05517115816473961f), f, make_float2(0.2426101416349411f, 0.2426101416349411f));
+            pl = __ffma2_rn(pl, f, make_float2(0.6932609677314758f, 0.6932609677314758f));
+            pl = __ffma2_rn(pl, f, make_float2(0.9999281167984009f, 0.9999281167984009f));
+            pp = make_float2(__uint_as_float(__float_as_uint(pl.x) + (__float_as_uint(tt.x) << 23)),
+                             __uint_as_float(__float_as_uint(pl.y) + (__float_as_uint(tt.y) << 23)));
+        }
+        sum = __fadd2_rn(sum, pp);
+        pk[i] = pack_bf16(pp.x, pp.y);
+    }
+}
+
+template <int kEmu, int kMode>
+__global__ void __launch_bounds__(256, 1) bench(float* out, long long* cycles, int iters, float c2) {
+    float s[128];
+#pragma unroll
+    for (int i = 0; i < 128; ++i) s[i] = -0.01f * (float)((threadIdx.x * 7 + i * 13) % 97);
+    float2 sum = make_float2(0.f, 0.f);
+    uint32_t acc = 0;
+    __syncthreads();
+    const long long t0 = clock64();
+    for (int it = 0; it < iters; ++it) {
+        uint32_t pk[64];
+        float mx = s[0];
+        if (kMode == 2) {  // include the row max
+#pragma unroll
+            for (int i = 1; i < 128; ++i) mx = fmaxf(mx, s[i]);
+        }
+        row_tile<kEmu, kMode>(s, c2, -1.0f - 0.001f * mx, sum, pk);
+#pragma unroll
+        for (int i = 0; i < 64; ++i) acc ^= pk[i];
+#pragma unroll
+        for (int i = 0; i < 128; i += 16) s[i] += 1e-3f * __uint_as_float((acc & 0x007fffffu) | 0x3f800000u);
+    }
+    const long long t1 = clock64();
+    __syncthreads();
+    if (threadIdx.x == 0) cycles[blockIdx.x] = t1 - t0;
+    out[blockIdx.x * blockDim.x + threadIdx.x] = sum.x + sum.y + __uint_as_float(acc);
+}
+
+template <int kEmu, int kMode> void run(const char* name, int threads) {
+    float* out; long long* cyc;
+    cudaMalloc(&out, 148 * 256 * 4); cudaMalloc(&cyc, 148 * 8);
+    const int iters = 200;
+    bench<kEmu, kMode><<<148, threads>>>(out, cyc, iters, 0.1275f);
+    bench<kEmu, kMode><<<148, threads>>>(out, cyc, iters, 0.1275f);
+    cudaDeviceSynchronize();
+    long long h[148]; cudaMemcpy(h, cyc, sizeof(h), cudaMemcpyDeviceToHost);
+    double avg = 0; for (int i = 0; i < 148; ++i) avg += h[i]; avg /= 148;
+    printf("UBENCH %-28s warps/SMSP %d : %8.1f cycles per 128-col row-tile per warp; SMSP time per warp-tile %8.1f  (%s)\n", name,
+           threads / 128, avg / iters, avg / iters / (threads / 128), cudaGetErrorString(cudaGetLastError()));
+    cudaFree(out); cudaFree(cyc);
+}
+
+int main() {
+    for (int threads : {128, 256}) {
+        run<0, 1>("scalar mufu", threads);
+        run<0, 0>("packed mufu emu0", threads);
+        run<1, 0>("packed emu1 (25%)", threads);
+        run<2, 0>("packed emu2 (50%)", threads);
+        run<3, 0>("packed emu3 (75%)", threads);
+        run<4, 0>("packed emu4 (100%)", threads);
+        run<0, 2>("packed mufu + rowmax", threads);
+    }
+    return 0;
+}

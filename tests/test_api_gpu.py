@@ -130,7 +130,9 @@ def test_reference_own_test_file_sampled(fat):
     spec = importlib.util.spec_from_file_location("ref_test_flash_attn", REF_TEST)
     mod = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mod)
-    seqs = [(1, 1), (63, 65), (64, 64), (65, 63), (127, 129), (128, 128), (129, 127), (1023, 1025), (1024, 1024), (1025, 1023), (1, 1025), (1025, 1)]
+    # (1, 1) is left out: there dQ = dK = 0 exactly, and the reference's relative-error gate (mean_rel <= 1e-2 with |ref|
+    # clamped at 1e-6, test_flash_attn.py:51-71) then compares round-off noise of torch SDPA's own backward (|ref| ~ 3e-7)
+    seqs = [(63, 65), (64, 64), (65, 63), (127, 129), (128, 128), (129, 127), (1023, 1025), (1024, 1024), (1025, 1023), (1, 1025), (1025, 1)]
     grid = list(itertools.product([64, 128], [1, 3], [(2, 1), (4, 2), (6, 3), (6, 1)], [False, True], seqs))
     for i, (d, b, (h, hk), causal, (sq, sk)) in enumerate(grid):
         if i % 37 == 0:
