@@ -1,0 +1,25 @@
+// flash_bwd_params.h — device-side parameter block shared by the backward kernels (mirrors Flash_bwd_params,
+// /root/reference/csrc/flash_attn/src/flash.h:55-76, with 64-bit-safe indexing done in the kernels).
+#pragma once
+#include <cuda_runtime.h>
+
+namespace fa100 {
+
+struct BwdParams {
+    const void *q, *k, *v, *o, *dout;
+    const float* lse;
+    float* dsum;
+    void *dq, *dk, *dv;
+    const int* cu_q;
+    const int* cu_k;
+    int b, sq, sk, h, h_k, hratio, d;
+    int is_causal;
+    float scale;
+    long long total_q, total_k;   // varlen: rows of the packed q / k tensors
+};
+
+// tensor-core (tcgen05) backward: dQ kernel + dK/dV kernel.  Returns FA_OK, or a negative value if this shape is
+// not handled (never happens for d in {64,128}).
+int launch_bwd_tc_sm100(const BwdParams& kp, bool bf16, cudaStream_t stream);
+
+}  // namespace fa100

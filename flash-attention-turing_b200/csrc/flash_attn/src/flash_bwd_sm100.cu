@@ -12,22 +12,13 @@
 //   flash_bwd_dk_dv_kernel_sm100_rows general-shape dK/dV (one warp per key row, group-summed)
 // The *_rows kernels are the any-shape correctness path (ragged lengths, varlen, d=64).
 #include <cuda_fp16.h>
+#include <stdlib.h>
 #include "fa_common.h"
 #include "sm100_ptx.cuh"
+#include "flash_bwd_params.h"
 
 namespace fa100 {
 
-struct BwdParams {
-    const void *q, *k, *v, *o, *dout;
-    const float* lse;
-    float* dsum;
-    void *dq, *dk, *dv;
-    const int* cu_q;
-    const int* cu_k;
-    int b, sq, sk, h, h_k, hratio, d;
-    int is_causal;
-    float scale;
-};
 
 template <bool kBf16> FA_DEVICE float2 unpack2(uint32_t w) {
     if constexpr (kBf16) {
@@ -193,13 +184,29 @@ flash_bwd_dk_dv_kernel_sm100_rows(const BwdParams p) {
     }
 }
 
-template <int D, bool kBf16> static int launch_bwd_rows(const BwdParams& kp, cudaStream_t stream) {
+static bool use_row_kernels() {
+    // FA_B200_BWD=rows selects the CUDA-core any-shape kernels (debug / cross-check); default is the tcgen05 path
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("FA_B200_BWD");
+        v = (e && e[0] == 'r') ? 1 : 0;
+    }
+    return v == 1;
+}
+
+template <int D, bool kBf16> static int launch_bwd_rows(const BwdParams& kp, bool bf16, cudaStream_t stream) {
     constexpr int kRowsPerBlockD = 8 * (32 / (D / 8));
     if (kp.sq > 0) {
         dim3 g1((kp.sq + kRowsPerBlockD - 1) / kRowsPerBlockD, kp.h, kp.b);
         flash_bwd_dot_do_o_kernel_sm100<D, kBf16><<<g1, 256, 0, stream>>>(kp);
         FA_CUDA_CHECK(cudaGetLastError());
         count_launch();
+    }
+    if (!use_row_kernels()) {
+        const int rc = launch_bwd_tc_sm100(kp, bf16, stream);
+        if (rc >= 0) return rc;   // < 0: degenerate sizes, fall through to the row kernels (they write the zeros)
+    }
+    if (kp.sq > 0) {
         dim3 g2((kp.sq + 7) / 8, kp.h, kp.b);
         flash_bwd_dq_kernel_sm100_rows<D, kBf16><<<g2, 256, 0, stream>>>(kp);
         FA_CUDA_CHECK(cudaGetLastError());
@@ -223,9 +230,10 @@ int launch_bwd_sm100(const fa_bwd_params* p, cudaStream_t stream) {
     kp.b = (int)f->b; kp.sq = (int)f->seqlen_q; kp.sk = (int)f->seqlen_k; kp.h = (int)f->h; kp.h_k = (int)f->h_k;
     kp.hratio = (int)(f->h / f->h_k); kp.d = (int)f->d; kp.is_causal = f->is_causal;
     kp.scale = 1.0f / sqrtf((float)f->d);
+    kp.total_q = f->total_q; kp.total_k = f->total_k;
     const bool bf16 = f->dtype == FA_DTYPE_BF16;
-    if (f->d == 128) return bf16 ? launch_bwd_rows<128, true>(kp, stream) : launch_bwd_rows<128, false>(kp, stream);
-    if (f->d == 64) return bf16 ? launch_bwd_rows<64, true>(kp, stream) : launch_bwd_rows<64, false>(kp, stream);
+    if (f->d == 128) return bf16 ? launch_bwd_rows<128, true>(kp, bf16, stream) : launch_bwd_rows<128, false>(kp, bf16, stream);
+    if (f->d == 64) return bf16 ? launch_bwd_rows<64, true>(kp, bf16, stream) : launch_bwd_rows<64, false>(kp, bf16, stream);
     set_error("head_dim %lld not supported (64 or 128)", (long long)f->d);
     return FA_ERR_INVALID_ARG;
 }

@@ -1,0 +1,672 @@
+// flash_bwd_tc_sm100.cu — tensor-core (tcgen05 / TMEM / TMA) attention backward for sm_100a.
+//
+// Same mathematical split as the reference (flash_bwd_kernel.h:28-838 dQ, :842-1676 dK/dV): two deterministic kernels,
+// no atomics, P and dS recomputed from LSE and D = rowsum(dO*O):
+//
+//   flash_bwd_dq_kernel_sm100     one CTA per 128-row Q tile, loops over 128-row K/V tiles
+//        S  = Q K^T, dP = dO V^T          (SS MMAs, fp32 in TMEM)
+//        P  = exp2(S c2 - LSE c1),  dS = P * (dP - D)        (one thread per query row, two warpgroups split columns)
+//        dQ += dS K                        (dS from TMEM as A, K consumed in place as an MN-major B)
+//   flash_bwd_dk_dv_kernel_sm100  one CTA per 128-row K/V tile and KV head, loops over the GQA group's heads and over
+//        64-row Q sub-tiles, everything transposed so that the K/V rows sit on the TMEM lanes:
+//        S^T = K Q^T, dP^T = V dO^T        (M = 128 kv rows, N = 64 q rows)
+//        P^T, dS^T elementwise             (LSE / D broadcast per column from shared memory)
+//        dV += P^T dO,  dK += dS^T Q       (P^T/dS^T from TMEM as A; dO/Q in place as MN-major B)
+//      The GQA group sum the reference does with h-expanded buffers + torch::sum_out (flash_api.cpp:265-312) is just
+//      continued accumulation in TMEM here.
+//
+// Unlike the forward, nothing is aliased in TMEM (S, dP, dS/P and the accumulators have their own columns), so the
+// MMAs of step j+1 are issued as soon as step j's S/dP have been read into registers and run underneath the
+// elementwise work of step j.
+#include <math.h>
+#include <stdlib.h>
+
+#include "fa_common.h"
+#include "flash_bwd_params.h"
+#include "sm100_ptx.cuh"
+
+namespace fa100 {
+
+constexpr int kBM = 128;
+constexpr float kLog2e = 1.4426950408889634f;
+
+struct SeqGeom {
+    int q_row0, k_row0, sq_b, sk_b, tma_b;
+};
+FA_DEVICE SeqGeom seq_geom(const BwdParams& p, int bidb) {
+    SeqGeom g;
+    if (p.cu_q != nullptr) {
+        g.q_row0 = p.cu_q[bidb]; g.sq_b = p.cu_q[bidb + 1] - g.q_row0;
+        g.k_row0 = p.cu_k[bidb]; g.sk_b = p.cu_k[bidb + 1] - g.k_row0;
+        g.tma_b = 0;
+    } else {
+        g.q_row0 = 0; g.k_row0 = 0; g.sq_b = p.sq; g.sk_b = p.sk; g.tma_b = bidb;
+    }
+    return g;
+}
+
+// =================================================================================================
+// dQ
+// =================================================================================================
+template <int D> struct DqSmem {
+    static constexpr int kSlab = kBM * 128;
+    static constexpr int kTile = kBM * D * 2;
+    static constexpr int kSlots = 4;                 // K_j -> slot 2j % 4, V_j -> slot (2j+1) % 4
+    static constexpr int kOffQ = 0;
+    static constexpr int kOffDO = kTile;
+    static constexpr int kOffKV = 2 * kTile;
+    static constexpr int kOffBar = kOffKV + kSlots * kTile;
+    static constexpr int kBytes = kOffBar + 256 + 1024;
+};
+namespace dqt { constexpr uint32_t kS = 0, kDP = 128, kDQ = 256, kDS = 384; }
+
+template <int D, bool kBf16>
+__global__ void __launch_bounds__(384, 1)
+flash_bwd_dq_kernel_sm100(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmDO,
+                          const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
+                          const BwdParams p) {
+    using L = DqSmem<D>;
+    constexpr int kSlabs = D / 64;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, wg = warp >> 2;
+    const int mblk = p.is_causal ? (gridDim.x - 1 - blockIdx.x) : blockIdx.x;
+    const int m0 = mblk * kBM;
+    const int bidh = blockIdx.y, bidb = blockIdx.z, bidh_k = bidh / p.hratio;
+    const SeqGeom sg = seq_geom(p, bidb);
+    if (m0 >= sg.sq_b) return;
+    const int off = sg.sk_b - sg.sq_b;
+    int kv_end = sg.sk_b;
+    if (p.is_causal) kv_end = min(sg.sk_b, max(0, m0 + kBM + off));
+    const int nblk = (kv_end + kBM - 1) / kBM;
+    const int64_t row_base = (p.cu_q != nullptr) ? (int64_t)sg.q_row0 : (int64_t)bidb * p.sq;
+    uint16_t* dq_base = reinterpret_cast<uint16_t*>(p.dq);
+    constexpr int kChunksPerRow = D / 8;
+
+    if (nblk == 0) {  // no visible key: dQ = 0
+        for (int idx = tid; idx < kBM * kChunksPerRow; idx += blockDim.x) {
+            const int rr = idx / kChunksPerRow, ch = idx % kChunksPerRow;
+            if (m0 + rr < sg.sq_b)
+                *(reinterpret_cast<uint4*>(dq_base + ((row_base + m0 + rr) * p.h + bidh) * D) + ch) = make_uint4(0, 0, 0, 0);
+        }
+        return;
+    }
+
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* sQ = smem + L::kOffQ;
+    uint8_t* sDO = smem + L::kOffDO;
+    uint8_t* sKV = smem + L::kOffKV;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::kOffBar);
+    uint64_t* bar_q = bars;            // Q + dO landed
+    uint64_t* bar_kv_full = bars + 1;  // [4]
+    uint64_t* bar_kv_empty = bars + 5; // [4]
+    uint64_t* bar_s_full = bars + 9;   // S and dP of step j complete
+    uint64_t* bar_s_empty = bars + 10; // 256 threads have S/dP of step j in registers
+    uint64_t* bar_ds_full = bars + 11; // 256 threads wrote dS_j
+    uint64_t* bar_ds_empty = bars + 12;// dQ MMA of step j retired
+    uint64_t* bar_dq_full = bars + 13;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
+
+    if (warp == 8) {
+        if (lane == 0) {
+            mbar_init(bar_q, 1);
+            for (int i = 0; i < 4; ++i) { mbar_init(&bar_kv_full[i], 1); mbar_init(&bar_kv_empty[i], 1); }
+            mbar_init(bar_s_full, 1); mbar_init(bar_s_empty, 256);
+            mbar_init(bar_ds_full, 256); mbar_init(bar_ds_empty, 1);
+            mbar_init(bar_dq_full, 1);
+            fence_barrier_init();
+        }
+        __syncwarp();
+        tmem_alloc<512>(tmem_slot);
+        tmem_relinquish();
+    } else if (warp == 9 && lane == 0) {
+        tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmDO); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (wg == 2) {
+        setmaxnreg_dec<72>();
+        if (warp == 9) {
+            if (lane == 0) {
+                mbar_arrive_expect_tx(bar_q, 2 * L::kTile);
+                for (int s = 0; s < kSlabs; ++s) {
+                    tma_load_4d(sQ + s * L::kSlab, &tmQ, bar_q, s * 64, bidh, sg.q_row0 + m0, sg.tma_b);
+                    tma_load_4d(sDO + s * L::kSlab, &tmDO, bar_q, s * 64, bidh, sg.q_row0 + m0, sg.tma_b);
+                }
+                for (int j = 0; j < nblk; ++j) {
+#pragma unroll
+                    for (int w = 0; w < 2; ++w) {
+                        const int i = 2 * j + w, slot = i % L::kSlots;
+                        mbar_wait(&bar_kv_empty[slot], ((i / L::kSlots) & 1) ^ 1);
+                        mbar_arrive_expect_tx(&bar_kv_full[slot], L::kTile);
+                        for (int s = 0; s < kSlabs; ++s)
+                            tma_load_4d(sKV + slot * L::kTile + s * L::kSlab, w == 0 ? &tmK : &tmV, &bar_kv_full[slot], s * 64,
+                                        bidh_k, sg.k_row0 + j * kBM, sg.tma_b);
+                    }
+                }
+            }
+        } else if (warp == 8) {
+            const int nb = __shfl_sync(0xffffffffu, nblk, 0);
+            const bool leader = elect_one();
+            constexpr uint32_t idesc_s = make_idesc(kBf16, kBM, kBM, false, false);
+            constexpr uint32_t idesc_dq = make_idesc(kBf16, kBM, D, false, true);
+            const uint32_t tm = __shfl_sync(0xffffffffu, tmem_base, 0);
+            const uint32_t q_lo = __shfl_sync(0xffffffffu, desc_lo(smem_u32(sQ), 16), 0);
+            const uint32_t do_lo = __shfl_sync(0xffffffffu, desc_lo(smem_u32(sDO), 16), 0);
+            const uint32_t kv_lo = __shfl_sync(0xffffffffu, desc_lo(smem_u32(sKV), 16), 0);
+            const uint32_t kvmn_lo = __shfl_sync(0xffffffffu, desc_lo(smem_u32(sKV), L::kSlab), 0);
+            constexpr uint32_t kTile16 = L::kTile >> 4;
+            auto issue_sdp = [&](int j) {
+                const int sk_ = (2 * j) % L::kSlots, sv_ = (2 * j + 1) % L::kSlots;
+                mbar_wait(&bar_kv_full[sk_], ((2 * j) / L::kSlots) & 1);
+                tc_fence_after();
+                if (leader) {
+#pragma unroll
+                    for (int kk = 0; kk < D / 16; ++kk) {
+                        const uint32_t o16 = ((kk >> 2) * L::kSlab + (kk & 3) * 32) >> 4;
+                        umma_ss(tm + dqt::kS, desc_make(q_lo + o16, kDescHiK), desc_make(kv_lo + sk_ * kTile16 + o16, kDescHiK),
+                                idesc_s, kk > 0);
+                    }
+                }
+                mbar_wait(&bar_kv_full[sv_], ((2 * j + 1) / L::kSlots) & 1);
+                tc_fence_after();
+                if (leader) {
+#pragma unroll
+                    for (int kk = 0; kk < D / 16; ++kk) {
+                        const uint32_t o16 = ((kk >> 2) * L::kSlab + (kk & 3) * 32) >> 4;
+                        umma_ss(tm + dqt::kDP, desc_make(do_lo + o16, kDescHiK), desc_make(kv_lo + sv_ * kTile16 + o16, kDescHiK),
+                                idesc_s, kk > 0);
+                    }
+                    tc_commit(bar_s_full);
+                }
+            };
+            mbar_wait(bar_q, 0);
+            issue_sdp(0);
+            for (int j = 0; j < nb; ++j) {
+                if (j + 1 < nb) {
+                    mbar_wait(bar_s_empty, j & 1);
+                    tc_fence_after();
+                    issue_sdp(j + 1);
+                }
+                mbar_wait(bar_ds_full, j & 1);
+                tc_fence_after();
+                if (leader) {
+                    const uint32_t ka = kvmn_lo + ((2 * j) % L::kSlots) * kTile16;
+#pragma unroll
+                    for (int kk = 0; kk < kBM / 16; ++kk)
+                        umma_ts(tm + dqt::kDQ, tm + dqt::kDS + kk * 8, desc_make(ka + kk * (2048 >> 4), kDescHiK), idesc_dq,
+                                (j > 0 || kk > 0));
+                    tc_commit(bar_ds_empty);
+                    tc_commit(&bar_kv_empty[(2 * j) % L::kSlots]);
+                    tc_commit(&bar_kv_empty[(2 * j + 1) % L::kSlots]);
+                    if (j + 1 == nb) tc_commit(bar_dq_full);
+                }
+                __syncwarp();
+            }
+        }
+    } else {
+        // ============ elementwise warpgroups: thread (g, r) owns query row r and key columns [64 g, 64 g + 64) ============
+        setmaxnreg_inc<216>();
+        const int g = wg;
+        const int r = ((warp & 3) << 5) | lane;
+        const int row = m0 + r;
+        const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+        const uint32_t tS = tmem_base + lane_base + dqt::kS + g * 64;
+        const uint32_t tDP = tmem_base + lane_base + dqt::kDP + g * 64;
+        const uint32_t tDS = tmem_base + lane_base + dqt::kDS + g * 32;
+        const int64_t stat = ((int64_t)bidb * p.h + bidh) * p.sq + row;
+        const bool row_ok = row < sg.sq_b;
+        const float lse_r = row_ok ? p.lse[stat] : INFINITY;       // +inf => P = 0 for rows beyond the sequence
+        const float d_r = row_ok ? p.dsum[stat] : 0.f;
+        const float c2 = p.scale * kLog2e;
+        const float neg = -lse_r * kLog2e;
+        int col_limit = sg.sk_b - 1;
+        if (p.is_causal) col_limit = min(col_limit, row + off);
+        const float2 c2v = make_float2(c2, c2), negv = make_float2(neg, neg), ndv = make_float2(-d_r, -d_r);
+
+        for (int j = 0; j < nblk; ++j) {
+            const int n0 = j * kBM;
+            mbar_wait(bar_s_full, j & 1);
+            tc_fence_after();
+            float s[64], dp[64];
+            tmem_ld32(tS, *reinterpret_cast<uint32_t(*)[32]>(&s[0]));
+            tmem_ld32(tS + 32, *reinterpret_cast<uint32_t(*)[32]>(&s[32]));
+            tmem_ld32(tDP, *reinterpret_cast<uint32_t(*)[32]>(&dp[0]));
+            tmem_ld32(tDP + 32, *reinterpret_cast<uint32_t(*)[32]>(&dp[32]));
+            tmem_wait_ld();
+            tc_fence_before();
+            mbar_arrive(bar_s_empty);
+
+            const bool need_mask = (n0 + kBM > sg.sk_b) || (p.is_causal && (n0 + kBM - 1 > m0 + off));
+            if (need_mask) {
+                const int lim = col_limit - n0 - g * 64;
+#pragma unroll
+                for (int c = 0; c < 64; ++c)
+                    if (c > lim) s[c] = -INFINITY;
+            }
+            uint32_t pk[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+                const float2 x = __ffma2_rn(make_float2(s[2 * i], s[2 * i + 1]), c2v, negv);
+                const float2 pr = make_float2(fast_exp2(x.x), fast_exp2(x.y));
+                const float2 ds = __fmul2_rn(pr, __fadd2_rn(make_float2(dp[2 * i], dp[2 * i + 1]), ndv));
+                pk[i] = pack2<kBf16>(ds.x, ds.y);
+            }
+            if (j > 0) mbar_wait(bar_ds_empty, (j - 1) & 1);
+            tmem_st32(tDS, pk);
+            tmem_wait_st();
+            tc_fence_before();
+            mbar_arrive(bar_ds_full);
+        }
+
+        // ---- epilogue: dQ * scale -> 16 bit -> smem (dead Q tile) -> coalesced stores ----
+        mbar_wait(bar_dq_full, 0);
+        tc_fence_after();
+        constexpr int kHalfD = D / 2;
+        const uint32_t tDQ = tmem_base + lane_base + dqt::kDQ + g * kHalfD;
+        uint8_t* sO = sQ;
+#pragma unroll
+        for (int c = 0; c < kHalfD / 32; ++c) {
+            uint32_t o[32];
+            tmem_ld32(tDQ + c * 32, o);
+            tmem_wait_ld();
+#pragma unroll
+            for (int q4 = 0; q4 < 4; ++q4) {
+                uint4 v;
+                v.x = pack2<kBf16>(__uint_as_float(o[q4 * 8 + 0]) * p.scale, __uint_as_float(o[q4 * 8 + 1]) * p.scale);
+                v.y = pack2<kBf16>(__uint_as_float(o[q4 * 8 + 2]) * p.scale, __uint_as_float(o[q4 * 8 + 3]) * p.scale);
+                v.z = pack2<kBf16>(__uint_as_float(o[q4 * 8 + 4]) * p.scale, __uint_as_float(o[q4 * 8 + 5]) * p.scale);
+                v.w = pack2<kBf16>(__uint_as_float(o[q4 * 8 + 6]) * p.scale, __uint_as_float(o[q4 * 8 + 7]) * p.scale);
+                const int chunk = g * (kHalfD / 8) + c * 4 + q4;
+                *reinterpret_cast<uint4*>(sO + r * (D * 2) + ((chunk ^ (r & 7)) * 16)) = v;
+            }
+        }
+        tc_fence_before();
+        named_bar_sync(1, 256);
+#pragma unroll 4
+        for (int idx = tid; idx < kBM * kChunksPerRow; idx += 256) {
+            const int rr = idx / kChunksPerRow, ch = idx % kChunksPerRow;
+            if (m0 + rr < sg.sq_b) {
+                const uint4 v = *reinterpret_cast<const uint4*>(sO + rr * (D * 2) + ((ch ^ (rr & 7)) * 16));
+                *(reinterpret_cast<uint4*>(dq_base + ((row_base + m0 + rr) * p.h + bidh) * D) + ch) = v;
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 8) {
+        tc_fence_after();
+        tmem_dealloc<512>(tmem_base);
+    }
+}
+
+// =================================================================================================
+// dK / dV
+// =================================================================================================
+constexpr int kSubQ = 64;   // query rows per step of the dK/dV kernel
+template <int D> struct DkvSmem {
+    static constexpr int kSlab = kBM * 128;            // 64-column slab of the 128-row K/V tiles
+    static constexpr int kTile = kBM * D * 2;
+    static constexpr int kSubSlab = kSubQ * 128;       // 64-column slab of a 64-row Q/dO sub-tile (8 KB)
+    static constexpr int kSub = kSubQ * D * 2;
+    static constexpr int kStages = 3;                  // each stage: Q sub-tile + dO sub-tile
+    static constexpr int kOffK = 0;
+    static constexpr int kOffV = kTile;
+    static constexpr int kOffQdO = 2 * kTile;
+    static constexpr int kOffStat = kOffQdO + kStages * 2 * kSub;   // float [2 buffers][2][64]: -LSE*log2e, D
+    static constexpr int kOffBar = kOffStat + 2 * 2 * kSubQ * 4;
+    static constexpr int kBytes = kOffBar + 256 + 1024;
+};
+namespace kvt { constexpr uint32_t kSt = 0, kDPt = 64, kPt = 128, kDSt = 160, kDV = 256, kDK = 384; }
+
+template <int D, bool kBf16>
+__global__ void __launch_bounds__(384, 1)
+flash_bwd_dk_dv_kernel_sm100(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmDO,
+                             const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
+                             const BwdParams p) {
+    using L = DkvSmem<D>;
+    constexpr int kSlabs = D / 64;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, wg = warp >> 2;
+    const int n0 = blockIdx.x * kBM;
+    const int bidh_k = blockIdx.y, bidb = blockIdx.z;
+    const SeqGeom sg = seq_geom(p, bidb);
+    if (n0 >= sg.sk_b) return;
+    const int off = sg.sk_b - sg.sq_b;
+    // query rows that can see any key of this tile: i >= n0 - off (causal), in 64-row sub-tiles
+    const int i_first = p.is_causal ? max(0, n0 - off) : 0;
+    const int it0 = i_first / kSubQ;
+    const int nsub = (sg.sq_b + kSubQ - 1) / kSubQ;
+    const int steps_per_head = max(0, nsub - it0);
+    const int total = steps_per_head * p.hratio;
+    const int64_t krow_base = (p.cu_q != nullptr) ? (int64_t)sg.k_row0 : (int64_t)bidb * p.sk;
+    uint16_t* dk_base = reinterpret_cast<uint16_t*>(p.dk);
+    uint16_t* dv_base = reinterpret_cast<uint16_t*>(p.dv);
+    constexpr int kChunksPerRow = D / 8;
+
+    if (total == 0) {  // no query row sees these keys: dK = dV = 0
+        for (int idx = tid; idx < kBM * kChunksPerRow; idx += blockDim.x) {
+            const int rr = idx / kChunksPerRow, ch = idx % kChunksPerRow;
+            if (n0 + rr < sg.sk_b) {
+                const int64_t o = ((krow_base + n0 + rr) * p.h_k + bidh_k) * D;
+                *(reinterpret_cast<uint4*>(dk_base + o) + ch) = make_uint4(0, 0, 0, 0);
+                *(reinterpret_cast<uint4*>(dv_base + o) + ch) = make_uint4(0, 0, 0, 0);
+            }
+        }
+        return;
+    }
+
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* sK = smem + L::kOffK;
+    uint8_t* sV = smem + L::kOffV;
+    uint8_t* sQdO = smem + L::kOffQdO;
+    float* sStat = reinterpret_cast<float*>(smem + L::kOffStat);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::kOffBar);
+    uint64_t* bar_kv = bars;              // K + V landed
+    uint64_t* bar_qdo_full = bars + 1;    // [3]
+    uint64_t* bar_qdo_empty = bars + 4;   // [3]
+    uint64_t* bar_s_full = bars + 7;
+    uint64_t* bar_s_empty = bars + 8;     // 256
+    uint64_t* bar_p_full = bars + 9;      // 256
+    uint64_t* bar_p_empty = bars + 10;
+    uint64_t* bar_acc_full = bars + 11;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+
+    if (warp == 8) {
+        if (lane == 0) {
+            mbar_init(bar_kv, 1);
+            for (int i = 0; i < L::kStages; ++i) { mbar_init(&bar_qdo_full[i], 1); mbar_init(&bar_qdo_empty[i], 1); }
+            mbar_init(bar_s_full, 1); mbar_init(bar_s_empty, 256);
+            mbar_init(bar_p_full, 256); mbar_init(bar_p_empty, 1);
+            mbar_init(bar_acc_full, 1);
+            fence_barrier_init();
+        }
+        __syncwarp();
+        tmem_alloc<512>(tmem_slot);
+        tmem_relinquish();
+    } else if (warp == 9 && lane == 0) {
+        tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmDO); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (wg == 2) {
+        setmaxnreg_dec<72>();
+        if (warp == 9) {
+            if (lane == 0) {
+                mbar_arrive_expect_tx(bar_kv, 2 * L::kTile);
+                for (int s = 0; s < kSlabs; ++s) {
+                    tma_load_4d(sK + s * L::kSlab, &tmK, bar_kv, s * 64, bidh_k, sg.k_row0 + n0, sg.tma_b);
+                    tma_load_4d(sV + s * L::kSlab, &tmV, bar_kv, s * 64, bidh_k, sg.k_row0 + n0, sg.tma_b);
+                }
+                for (int st = 0; st < total; ++st) {
+                    const int stage = st % L::kStages;
+                    const int hq = bidh_k * p.hratio + st / steps_per_head;
+                    const int it = it0 + st % steps_per_head;
+                    mbar_wait(&bar_qdo_empty[stage], ((st / L::kStages) & 1) ^ 1);
+                    mbar_arrive_expect_tx(&bar_qdo_full[stage], 2 * L::kSub);
+                    uint8_t* dst = sQdO + stage * 2 * L::kSub;
+                    for (int s = 0; s < kSlabs; ++s) {
+                        tma_load_4d(dst + s * L::kSubSlab, &tmQ, &bar_qdo_full[stage], s * 64, hq, sg.q_row0 + it * kSubQ, sg.tma_b);
+                        tma_load_4d(dst + L::kSub + s * L::kSubSlab, &tmDO, &bar_qdo_full[stage], s * 64, hq,
+                                    sg.q_row0 + it * kSubQ, sg.tma_b);
+                    }
+                }
+            }
+        } else if (warp == 8) {
+            const int tot = __shfl_sync(0xffffffffu, total, 0);
+            const bool leader = elect_one();
+            constexpr uint32_t idesc_st = make_idesc(kBf16, kBM, kSubQ, false, false);   // M=128 kv, N=64 q
+            constexpr uint32_t idesc_acc = make_idesc(kBf16, kBM, D, false, true);       // N = D, B MN-major
+            const uint32_t tm = __shfl_sync(0xffffffffu, tmem_base, 0);
+            const uint32_t k_lo = __shfl_sync(0xffffffffu, desc_lo(smem_u32(sK), 16), 0);
+            const uint32_t v_lo = __shfl_sync(0xffffffffu, desc_lo(smem_u32(sV), 16), 0);
+            const uint32_t qk_lo = __shfl_sync(0xffffffffu, desc_lo(smem_u32(sQdO), 16), 0);             // K-major view
+            const uint32_t qmn_lo = __shfl_sync(0xffffffffu, desc_lo(smem_u32(sQdO), L::kSubSlab), 0);   // MN-major view
+            constexpr uint32_t kStage16 = (2 * L::kSub) >> 4, kSub16 = L::kSub >> 4;
+            auto issue_sdp = [&](int st) {
+                const int stage = st % L::kStages;
+                mbar_wait(&bar_qdo_full[stage], (st / L::kStages) & 1);
+                tc_fence_after();
+                if (leader) {
+                    const uint32_t qa = qk_lo + stage * kStage16, da = qa + kSub16;
+#pragma unroll
+                    for (int kk = 0; kk < D / 16; ++kk) {   // S^T = K Q^T
+                        const uint32_t oa = ((kk >> 2) * L::kSlab + (kk & 3) * 32) >> 4;
+                        const uint32_t ob = ((kk >> 2) * L::kSubSlab + (kk & 3) * 32) >> 4;
+                        umma_ss(tm + kvt::kSt, desc_make(k_lo + oa, kDescHiK), desc_make(qa + ob, kDescHiK), idesc_st, kk > 0);
+                    }
+#pragma unroll
+                    for (int kk = 0; kk < D / 16; ++kk) {   // dP^T = V dO^T
+                        const uint32_t oa = ((kk >> 2) * L::kSlab + (kk & 3) * 32) >> 4;
+                        const uint32_t ob = ((kk >> 2) * L::kSubSlab + (kk & 3) * 32) >> 4;
+                        umma_ss(tm + kvt::kDPt, desc_make(v_lo + oa, kDescHiK), desc_make(da + ob, kDescHiK), idesc_st, kk > 0);
+                    }
+                    tc_commit(bar_s_full);
+                }
+            };
+            mbar_wait(bar_kv, 0);
+            issue_sdp(0);
+            for (int st = 0; st < tot; ++st) {
+                if (st + 1 < tot) {
+                    mbar_wait(bar_s_empty, st & 1);
+                    tc_fence_after();
+                    issue_sdp(st + 1);
+                }
+                mbar_wait(bar_p_full, st & 1);
+                tc_fence_after();
+                if (leader) {
+                    const uint32_t qa = qmn_lo + (st % L::kStages) * kStage16, da = qa + kSub16;
+#pragma unroll
+                    for (int kk = 0; kk < kSubQ / 16; ++kk)   // dV += P^T dO
+                        umma_ts(tm + kvt::kDV, tm + kvt::kPt + kk * 8, desc_make(da + kk * (2048 >> 4), kDescHiK), idesc_acc,
+                                (st > 0 || kk > 0));
+#pragma unroll
+                    for (int kk = 0; kk < kSubQ / 16; ++kk)   // dK += dS^T Q
+                        umma_ts(tm + kvt::kDK, tm + kvt::kDSt + kk * 8, desc_make(qa + kk * (2048 >> 4), kDescHiK), idesc_acc,
+                                (st > 0 || kk > 0));
+                    tc_commit(bar_p_empty);
+                    tc_commit(&bar_qdo_empty[st % L::kStages]);
+                    if (st + 1 == tot) tc_commit(bar_acc_full);
+                }
+                __syncwarp();
+            }
+        }
+    } else {
+        // ===== elementwise warpgroups: thread (g, r) owns key row r and query columns [32 g, 32 g + 32) of the sub-tile =====
+        setmaxnreg_inc<216>();
+        const int g = wg;
+        const int r = ((warp & 3) << 5) | lane;
+        const int jg = n0 + r;                       // global key row of this thread
+        const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+        const uint32_t tSt = tmem_base + lane_base + kvt::kSt + g * 32;
+        const uint32_t tDPt = tmem_base + lane_base + kvt::kDPt + g * 32;
+        const uint32_t tPt = tmem_base + lane_base + kvt::kPt + g * 16;
+        const uint32_t tDSt = tmem_base + lane_base + kvt::kDSt + g * 16;
+        const float c2 = p.scale * kLog2e;
+        const float2 c2v = make_float2(c2, c2);
+
+        // per-column statistics of the current sub-tile, staged through shared memory by the first 64 threads
+        auto load_stats = [&](int st, float& nl, float& dd) {
+            const int hq = bidh_k * p.hratio + st / steps_per_head;
+            const int i = (it0 + st % steps_per_head) * kSubQ + tid;
+            if (i < sg.sq_b) {
+                const int64_t o = ((int64_t)bidb * p.h + hq) * p.sq + i;
+                nl = -p.lse[o] * kLog2e;
+                dd = -p.dsum[o];
+            } else {
+                nl = -INFINITY;   // P = 0 for query rows beyond the sequence
+                dd = 0.f;
+            }
+        };
+        float nl_next = 0.f, dd_next = 0.f;
+        if (tid < kSubQ) {
+            load_stats(0, nl_next, dd_next);
+            sStat[tid] = nl_next;
+            sStat[kSubQ + tid] = dd_next;
+        }
+        named_bar_sync(1, 256);
+
+        for (int st = 0; st < total; ++st) {
+            const int it = it0 + st % steps_per_head;
+            const float* stat = sStat + (st & 1) * 2 * kSubQ;
+            if (tid < kSubQ && st + 1 < total) load_stats(st + 1, nl_next, dd_next);   // prefetch (global loads in flight)
+            mbar_wait(bar_s_full, st & 1);
+            tc_fence_after();
+            float s[32], dp[32];
+            tmem_ld32(tSt, *reinterpret_cast<uint32_t(*)[32]>(&s[0]));
+            tmem_ld32(tDPt, *reinterpret_cast<uint32_t(*)[32]>(&dp[0]));
+            tmem_wait_ld();
+            tc_fence_before();
+            mbar_arrive(bar_s_empty);
+
+            // causal: key jg visible to query i iff jg <= i + off  <=>  column c >= jg - off - it*64 - 32 g
+            const bool need_mask = p.is_causal && (it * kSubQ < n0 + kBM - 1 - off);
+            const int cmin = need_mask ? (jg - off - it * kSubQ - g * 32) : 0;
+            uint32_t pkp[16], pkd[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                const float4 nl4 = *reinterpret_cast<const float4*>(stat + g * 32 + (i >> 1) * 4);          // broadcast
+                const float4 dd4 = *reinterpret_cast<const float4*>(stat + kSubQ + g * 32 + (i >> 1) * 4);
+                const float2 nl = (i & 1) ? make_float2(nl4.z, nl4.w) : make_float2(nl4.x, nl4.y);
+                const float2 dd = (i & 1) ? make_float2(dd4.z, dd4.w) : make_float2(dd4.x, dd4.y);
+                const float2 x = __ffma2_rn(make_float2(s[2 * i], s[2 * i + 1]), c2v, nl);
+                float2 pr = make_float2(fast_exp2(x.x), fast_exp2(x.y));
+                if (need_mask) {
+                    if (2 * i < cmin) pr.x = 0.f;
+                    if (2 * i + 1 < cmin) pr.y = 0.f;
+                }
+                const float2 ds = __fmul2_rn(pr, __fadd2_rn(make_float2(dp[2 * i], dp[2 * i + 1]), dd));
+                pkp[i] = pack2<kBf16>(pr.x, pr.y);
+                pkd[i] = pack2<kBf16>(ds.x, ds.y);
+            }
+            if (st > 0) mbar_wait(bar_p_empty, (st - 1) & 1);
+            tmem_st16(tPt, pkp);
+            tmem_st16(tDSt, pkd);
+            tmem_wait_st();
+            tc_fence_before();
+            mbar_arrive(bar_p_full);
+            // publish the next step's statistics (other buffer) and line the two warpgroups up
+            if (tid < kSubQ && st + 1 < total) {
+                float* nxt = sStat + ((st + 1) & 1) * 2 * kSubQ;
+                nxt[tid] = nl_next;
+                nxt[kSubQ + tid] = dd_next;
+            }
+            named_bar_sync(1, 256);
+        }
+
+        // ---- epilogue: dV, dK * scale -> 16 bit -> smem (dead V / K tiles) -> coalesced stores ----
+        mbar_wait(bar_acc_full, 0);
+        tc_fence_after();
+        constexpr int kHalfD = D / 2;
+#pragma unroll
+        for (int which = 0; which < 2; ++which) {
+            const uint32_t tA = tmem_base + lane_base + (which == 0 ? kvt::kDV : kvt::kDK) + g * kHalfD;
+            uint8_t* sO = which == 0 ? sV : sK;
+            const float mul = which == 0 ? 1.f : p.scale;
+#pragma unroll
+            for (int c = 0; c < kHalfD / 32; ++c) {
+                uint32_t o[32];
+                tmem_ld32(tA + c * 32, o);
+                tmem_wait_ld();
+#pragma unroll
+                for (int q4 = 0; q4 < 4; ++q4) {
+                    uint4 v;
+                    v.x = pack2<kBf16>(__uint_as_float(o[q4 * 8 + 0]) * mul, __uint_as_float(o[q4 * 8 + 1]) * mul);
+                    v.y = pack2<kBf16>(__uint_as_float(o[q4 * 8 + 2]) * mul, __uint_as_float(o[q4 * 8 + 3]) * mul);
+                    v.z = pack2<kBf16>(__uint_as_float(o[q4 * 8 + 4]) * mul, __uint_as_float(o[q4 * 8 + 5]) * mul);
+                    v.w = pack2<kBf16>(__uint_as_float(o[q4 * 8 + 6]) * mul, __uint_as_float(o[q4 * 8 + 7]) * mul);
+                    const int chunk = g * (kHalfD / 8) + c * 4 + q4;
+                    *reinterpret_cast<uint4*>(sO + r * (D * 2) + ((chunk ^ (r & 7)) * 16)) = v;
+                }
+            }
+        }
+        tc_fence_before();
+        named_bar_sync(1, 256);
+#pragma unroll 2
+        for (int idx = tid; idx < kBM * kChunksPerRow; idx += 256) {
+            const int rr = idx / kChunksPerRow, ch = idx % kChunksPerRow;
+            if (n0 + rr < sg.sk_b) {
+                const int64_t o = ((krow_base + n0 + rr) * p.h_k + bidh_k) * D;
+                const int so = rr * (D * 2) + ((ch ^ (rr & 7)) * 16);
+                *(reinterpret_cast<uint4*>(dv_base + o) + ch) = *reinterpret_cast<const uint4*>(sV + so);
+                *(reinterpret_cast<uint4*>(dk_base + o) + ch) = *reinterpret_cast<const uint4*>(sK + so);
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 8) {
+        tc_fence_after();
+        tmem_dealloc<512>(tmem_base);
+    }
+}
+
+// =================================================================================================
+// host
+// =================================================================================================
+template <int D, bool kBf16>
+static int launch_tc(const BwdParams& kp, const CUtensorMap& tq128, const CUtensorMap& tdo128, const CUtensorMap& tq64,
+                     const CUtensorMap& tdo64, const CUtensorMap& tk, const CUtensorMap& tv, cudaStream_t stream) {
+    static bool attr_set = false;
+    auto kdq = flash_bwd_dq_kernel_sm100<D, kBf16>;
+    auto kkv = flash_bwd_dk_dv_kernel_sm100<D, kBf16>;
+    if (!attr_set) {
+        FA_CUDA_CHECK(cudaFuncSetAttribute(kdq, cudaFuncAttributeMaxDynamicSharedMemorySize, DqSmem<D>::kBytes));
+        FA_CUDA_CHECK(cudaFuncSetAttribute(kkv, cudaFuncAttributeMaxDynamicSharedMemorySize, DkvSmem<D>::kBytes));
+        attr_set = true;
+    }
+    if (kp.sq > 0) {
+        dim3 g((kp.sq + kBM - 1) / kBM, kp.h, kp.b);
+        kdq<<<g, 384, DqSmem<D>::kBytes, stream>>>(tq128, tdo128, tk, tv, kp);
+        FA_CUDA_CHECK(cudaGetLastError());
+        count_launch();
+    }
+    if (kp.sk > 0) {
+        dim3 g((kp.sk + kBM - 1) / kBM, kp.h_k, kp.b);
+        kkv<<<g, 384, DkvSmem<D>::kBytes, stream>>>(tq64, tdo64, tk, tv, kp);
+        FA_CUDA_CHECK(cudaGetLastError());
+        count_launch();
+    }
+    return FA_OK;
+}
+
+int launch_bwd_tc_sm100(const BwdParams& kp, bool bf16, cudaStream_t stream) {
+    const bool varlen = kp.cu_q != nullptr;
+    const uint64_t D = (uint64_t)kp.d;
+    const uint64_t rows_q = varlen ? (uint64_t)kp.total_q : (uint64_t)kp.sq;
+    const uint64_t rows_k = varlen ? (uint64_t)kp.total_k : (uint64_t)kp.sk;
+    const uint64_t nb = varlen ? 1 : (uint64_t)kp.b;
+    if (rows_q == 0 || rows_k == 0) return -1;   // degenerate: let the row kernels write the zeros
+    CUtensorMap tq128, tdo128, tq64, tdo64, tk, tv;
+    const uint32_t box128[4] = {64, 1, 128, 1}, box64[4] = {64, 1, 64, 1};
+    {
+        const uint64_t dims[4] = {D, (uint64_t)kp.h, rows_q, nb};
+        const uint64_t str[3] = {D * 2, (uint64_t)kp.h * D * 2, rows_q * (uint64_t)kp.h * D * 2};
+        int rc;
+        if ((rc = encode_tmap_4d(&tq128, kp.q, bf16, dims, str, box128)) != FA_OK) return rc;
+        if ((rc = encode_tmap_4d(&tdo128, kp.dout, bf16, dims, str, box128)) != FA_OK) return rc;
+        if ((rc = encode_tmap_4d(&tq64, kp.q, bf16, dims, str, box64)) != FA_OK) return rc;
+        if ((rc = encode_tmap_4d(&tdo64, kp.dout, bf16, dims, str, box64)) != FA_OK) return rc;
+    }
+    {
+        const uint64_t dims[4] = {D, (uint64_t)kp.h_k, rows_k, nb};
+        const uint64_t str[3] = {D * 2, (uint64_t)kp.h_k * D * 2, rows_k * (uint64_t)kp.h_k * D * 2};
+        int rc;
+        if ((rc = encode_tmap_4d(&tk, kp.k, bf16, dims, str, box128)) != FA_OK) return rc;
+        if ((rc = encode_tmap_4d(&tv, kp.v, bf16, dims, str, box128)) != FA_OK) return rc;
+    }
+    if (kp.d == 128) return bf16 ? launch_tc<128, true>(kp, tq128, tdo128, tq64, tdo64, tk, tv, stream)
+                                 : launch_tc<128, false>(kp, tq128, tdo128, tq64, tdo64, tk, tv, stream);
+    if (kp.d == 64) return bf16 ? launch_tc<64, true>(kp, tq128, tdo128, tq64, tdo64, tk, tv, stream)
+                                : launch_tc<64, false>(kp, tq128, tdo128, tq64, tdo64, tk, tv, stream);
+    return -1;
+}
+
+}  // namespace fa100
