@@ -66,4 +66,6 @@ def flash_attn_func(q, k, v, *legacy_dims, causal: bool = False):
     return _FlashAttnFunc.apply(q, k, v, bool(causal))
 
 
-__all__ = ["fwd", "bwd", "varlen_fwd", "varlen_bwd", "flash_attn_func", "last_launch_count", "LIB_PATH"]
+from . import sharded  # noqa: E402,F401  (batch-shard runner for multi-GPU boxes)
+
+__all__ = ["fwd", "bwd", "varlen_fwd", "varlen_bwd", "flash_attn_func", "last_launch_count", "LIB_PATH", "sharded"]

@@ -1,0 +1,82 @@
+"""Batch-shard runner: the (batch x head) attention problems are independent, so N GPUs each take a contiguous slab of
+the batch dimension and run the single-GPU kernels — no collective on the data path.  torch.distributed
+is used only to move slabs when the caller holds the whole batch on one rank (scatter Q/K/V, gather O) and lives outside
+any timed region.  The reference has no multi-GPU support at all (its int32 offsets overflow on the unsharded config 5,
+block_info.h:15-21).
+
+The compute callable is injected so that the host logic can be exercised on CPU (gloo) in tests; in production it is
+flash_attn_turing.fwd.
+"""
+from __future__ import annotations
+
+from typing import Callable, List, Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def shard_ranges(batch: int, world_size: int) -> List[Tuple[int, int]]:
+    """contiguous [start, end) batch ranges per rank; the first `batch % world_size` ranks get one extra"""
+    base, extra = divmod(batch, world_size)
+    out, s = [], 0
+    for r in range(world_size):
+        e = s + base + (1 if r < extra else 0)
+        out.append((s, e))
+        s = e
+    return out
+
+
+def scatter_batch(x: Optional[torch.Tensor], shape, dtype, device, src: int = 0, group=None) -> torch.Tensor:
+    """rank `src` holds x [b, ...]; every rank returns its slab [b_r, ...] (contiguous slices: zero repacking)"""
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    ranges = shard_ranges(shape[0], world)
+    s, e = ranges[rank]
+    out = torch.empty((e - s,) + tuple(shape[1:]), dtype=dtype, device=device)
+    if rank == src:
+        reqs = []
+        for r, (rs, re) in enumerate(ranges):
+            if r == src:
+                out.copy_(x[rs:re])
+            elif re > rs:
+                reqs.append(dist.isend(x[rs:re].contiguous(), dst=r, group=group))
+        for q in reqs:
+            q.wait()
+    elif e > s:
+        dist.recv(out, src=src, group=group)
+    return out
+
+
+def gather_batch(x_local: torch.Tensor, batch: int, dst: int = 0, group=None) -> Optional[torch.Tensor]:
+    """inverse of scatter_batch: rank `dst` returns the full [b, ...] tensor, others None"""
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    ranges = shard_ranges(batch, world)
+    if rank == dst:
+        full = torch.empty((batch,) + tuple(x_local.shape[1:]), dtype=x_local.dtype, device=x_local.device)
+        for r, (rs, re) in enumerate(ranges):
+            if r == dst:
+                full[rs:re].copy_(x_local)
+            elif re > rs:
+                dist.recv(full[rs:re], src=r, group=group)
+        return full
+    if x_local.shape[0] > 0:
+        dist.send(x_local.contiguous(), dst=dst, group=group)
+    return None
+
+
+def fwd_sharded(q, k, v, is_causal: bool, fwd_fn: Callable, shapes=None, dtype=None, device=None, src: int = 0, group=None):
+    """Full-batch forward across the ranks of `group`.  On rank `src` q,k,v are the full tensors (None elsewhere, then
+    `shapes` = (q.shape, k.shape), dtype and device must be given).  Returns (o, l) on rank `src`, (None, None) elsewhere."""
+    rank = dist.get_rank(group)
+    if rank == src:
+        shapes, dtype, device = (tuple(q.shape), tuple(k.shape)), q.dtype, q.device
+    ql = scatter_batch(q, shapes[0], dtype, device, src, group)
+    kl = scatter_batch(k, shapes[1], dtype, device, src, group)
+    vl = scatter_batch(v, shapes[1], dtype, device, src, group)
+    if ql.shape[0] > 0:
+        ol, ll = fwd_fn(ql, kl, vl, is_causal)
+    else:
+        ol = ql
+        ll = torch.empty((0, shapes[0][2], shapes[0][1]), dtype=torch.float32, device=device)
+    o = gather_batch(ol, shapes[0][0], src, group)
+    l = gather_batch(ll, shapes[0][0], src, group)
+    return o, l
