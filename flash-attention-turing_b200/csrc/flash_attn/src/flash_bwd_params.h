@@ -16,7 +16,18 @@ struct BwdParams {
     int is_causal;
     float scale;
     long long total_q, total_k;   // varlen: rows of the packed q / k tensors
+    long long* trace;             // FA_TRACE builds only
 };
+
+#ifdef FA_TRACE
+#define FA_BTRACE(role, j, ev)                                                                   \
+    do {                                                                                         \
+        if (p.trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && (j) < 64)        \
+            p.trace[((role) * 64 + (j)) * 8 + (ev)] = clock64();                                 \
+    } while (0)
+#else
+#define FA_BTRACE(role, j, ev) do {} while (0)
+#endif
 
 // tensor-core (tcgen05) backward: dQ kernel + dK/dV kernel.  Returns FA_OK, or a negative value if this shape is
 // not handled (never happens for d in {64,128}).

@@ -230,7 +230,7 @@ int launch_bwd_sm100(const fa_bwd_params* p, cudaStream_t stream) {
     kp.b = (int)f->b; kp.sq = (int)f->seqlen_q; kp.sk = (int)f->seqlen_k; kp.h = (int)f->h; kp.h_k = (int)f->h_k;
     kp.hratio = (int)(f->h / f->h_k); kp.d = (int)f->d; kp.is_causal = f->is_causal;
     kp.scale = 1.0f / sqrtf((float)f->d);
-    kp.total_q = f->total_q; kp.total_k = f->total_k;
+    kp.total_q = f->total_q; kp.total_k = f->total_k; kp.trace = nullptr;
     const bool bf16 = f->dtype == FA_DTYPE_BF16;
     if (f->d == 128) return bf16 ? launch_bwd_rows<128, true>(kp, bf16, stream) : launch_bwd_rows<128, false>(kp, bf16, stream);
     if (f->d == 64) return bf16 ? launch_bwd_rows<64, true>(kp, bf16, stream) : launch_bwd_rows<64, false>(kp, bf16, stream);

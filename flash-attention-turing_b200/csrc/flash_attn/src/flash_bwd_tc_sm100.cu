@@ -51,12 +51,14 @@ FA_DEVICE SeqGeom seq_geom(const BwdParams& p, int bidb) {
 template <int D> struct DqSmem {
     static constexpr int kSlab = kBM * 128;
     static constexpr int kTile = kBM * D * 2;
-    static constexpr int kSlots = 4;                 // K_j -> slot 2j % 4, V_j -> slot (2j+1) % 4
+    static constexpr int kKStages = 3;               // K_j is needed until dQ_j retires -> 3 deep
+    static constexpr int kVStages = 2;               // V_j is released as soon as dP_j retires -> 2 deep
     static constexpr int kOffQ = 0;
     static constexpr int kOffDO = kTile;
-    static constexpr int kOffKV = 2 * kTile;
-    static constexpr int kOffBar = kOffKV + kSlots * kTile;
-    static constexpr int kBytes = kOffBar + 256 + 1024;
+    static constexpr int kOffK = 2 * kTile;
+    static constexpr int kOffV = kOffK + kKStages * kTile;
+    static constexpr int kOffBar = kOffV + kVStages * kTile;
+    static constexpr int kBytes = kOffBar + 256 + 1024;   // 224 KB of tiles + barriers at D = 128
 };
 namespace dqt { constexpr uint32_t kS = 0, kDP = 128, kDQ = 256, kDS = 384; }
 
@@ -94,22 +96,26 @@ flash_bwd_dq_kernel_sm100(const __grid_constant__ CUtensorMap tmQ, const __grid_
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* sQ = smem + L::kOffQ;
     uint8_t* sDO = smem + L::kOffDO;
-    uint8_t* sKV = smem + L::kOffKV;
+    uint8_t* sK = smem + L::kOffK;
+    uint8_t* sV = smem + L::kOffV;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::kOffBar);
     uint64_t* bar_q = bars;            // Q + dO landed
-    uint64_t* bar_kv_full = bars + 1;  // [4]
-    uint64_t* bar_kv_empty = bars + 5; // [4]
-    uint64_t* bar_s_full = bars + 9;   // S and dP of step j complete
-    uint64_t* bar_s_empty = bars + 10; // 256 threads have S/dP of step j in registers
-    uint64_t* bar_ds_full = bars + 11; // 256 threads wrote dS_j
-    uint64_t* bar_ds_empty = bars + 12;// dQ MMA of step j retired
-    uint64_t* bar_dq_full = bars + 13;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
+    uint64_t* bar_k_full = bars + 1;   // [3]
+    uint64_t* bar_k_empty = bars + 4;  // [3]
+    uint64_t* bar_v_full = bars + 7;   // [2]
+    uint64_t* bar_v_empty = bars + 9;  // [2]
+    uint64_t* bar_s_full = bars + 11;  // S and dP of step j complete
+    uint64_t* bar_s_empty = bars + 12; // 256 threads have S/dP of step j in registers
+    uint64_t* bar_ds_full = bars + 13; // 256 threads wrote dS_j
+    uint64_t* bar_ds_empty = bars + 14;// dQ MMA of step j retired
+    uint64_t* bar_dq_full = bars + 15;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
 
     if (warp == 8) {
         if (lane == 0) {
             mbar_init(bar_q, 1);
-            for (int i = 0; i < 4; ++i) { mbar_init(&bar_kv_full[i], 1); mbar_init(&bar_kv_empty[i], 1); }
+            for (int i = 0; i < L::kKStages; ++i) { mbar_init(&bar_k_full[i], 1); mbar_init(&bar_k_empty[i], 1); }
+            for (int i = 0; i < L::kVStages; ++i) { mbar_init(&bar_v_full[i], 1); mbar_init(&bar_v_empty[i], 1); }
             mbar_init(bar_s_full, 1); mbar_init(bar_s_empty, 256);
             mbar_init(bar_ds_full, 256); mbar_init(bar_ds_empty, 1);
             mbar_init(bar_dq_full, 1);
@@ -136,15 +142,15 @@ flash_bwd_dq_kernel_sm100(const __grid_constant__ CUtensorMap tmQ, const __grid_
                     tma_load_4d(sDO + s * L::kSlab, &tmDO, bar_q, s * 64, bidh, sg.q_row0 + m0, sg.tma_b);
                 }
                 for (int j = 0; j < nblk; ++j) {
-#pragma unroll
-                    for (int w = 0; w < 2; ++w) {
-                        const int i = 2 * j + w, slot = i % L::kSlots;
-                        mbar_wait(&bar_kv_empty[slot], ((i / L::kSlots) & 1) ^ 1);
-                        mbar_arrive_expect_tx(&bar_kv_full[slot], L::kTile);
-                        for (int s = 0; s < kSlabs; ++s)
-                            tma_load_4d(sKV + slot * L::kTile + s * L::kSlab, w == 0 ? &tmK : &tmV, &bar_kv_full[slot], s * 64,
-                                        bidh_k, sg.k_row0 + j * kBM, sg.tma_b);
-                    }
+                    const int ks = j % L::kKStages, vs = j % L::kVStages;
+                    mbar_wait(&bar_k_empty[ks], ((j / L::kKStages) & 1) ^ 1);
+                    mbar_arrive_expect_tx(&bar_k_full[ks], L::kTile);
+                    for (int s = 0; s < kSlabs; ++s)
+                        tma_load_4d(sK + ks * L::kTile + s * L::kSlab, &tmK, &bar_k_full[ks], s * 64, bidh_k, sg.k_row0 + j * kBM, sg.tma_b);
+                    mbar_wait(&bar_v_empty[vs], ((j / L::kVStages) & 1) ^ 1);
+                    mbar_arrive_expect_tx(&bar_v_full[vs], L::kTile);
+                    for (int s = 0; s < kSlabs; ++s)
+                        tma_load_4d(sV + vs * L::kTile + s * L::kSlab, &tmV, &bar_v_full[vs], s * 64, bidh_k, sg.k_row0 + j * kBM, sg.tma_b);
                 }
             }
         } else if (warp == 8) {
@@ -155,31 +161,33 @@ flash_bwd_dq_kernel_sm100(const __grid_constant__ CUtensorMap tmQ, const __grid_
             const uint32_t tm = __shfl_sync(0xffffffffu, tmem_base, 0);
             const uint32_t q_lo = __shfl_sync(0xffffffffu, desc_lo(smem_u32(sQ), 16), 0);
             const uint32_t do_lo = __shfl_sync(0xffffffffu, desc_lo(smem_u32(sDO), 16), 0);
-            const uint32_t kv_lo = __shfl_sync(0xffffffffu, desc_lo(smem_u32(sKV), 16), 0);
-            const uint32_t kvmn_lo = __shfl_sync(0xffffffffu, desc_lo(smem_u32(sKV), L::kSlab), 0);
+            const uint32_t k_lo = __shfl_sync(0xffffffffu, desc_lo(smem_u32(sK), 16), 0);
+            const uint32_t v_lo = __shfl_sync(0xffffffffu, desc_lo(smem_u32(sV), 16), 0);
+            const uint32_t kmn_lo = __shfl_sync(0xffffffffu, desc_lo(smem_u32(sK), L::kSlab), 0);
             constexpr uint32_t kTile16 = L::kTile >> 4;
             auto issue_sdp = [&](int j) {
-                const int sk_ = (2 * j) % L::kSlots, sv_ = (2 * j + 1) % L::kSlots;
-                mbar_wait(&bar_kv_full[sk_], ((2 * j) / L::kSlots) & 1);
+                const int sk_ = j % L::kKStages, sv_ = j % L::kVStages;
+                mbar_wait(&bar_k_full[sk_], (j / L::kKStages) & 1);
                 tc_fence_after();
                 if (leader) {
 #pragma unroll
                     for (int kk = 0; kk < D / 16; ++kk) {
                         const uint32_t o16 = ((kk >> 2) * L::kSlab + (kk & 3) * 32) >> 4;
-                        umma_ss(tm + dqt::kS, desc_make(q_lo + o16, kDescHiK), desc_make(kv_lo + sk_ * kTile16 + o16, kDescHiK),
+                        umma_ss(tm + dqt::kS, desc_make(q_lo + o16, kDescHiK), desc_make(k_lo + sk_ * kTile16 + o16, kDescHiK),
                                 idesc_s, kk > 0);
                     }
                 }
-                mbar_wait(&bar_kv_full[sv_], ((2 * j + 1) / L::kSlots) & 1);
+                mbar_wait(&bar_v_full[sv_], (j / L::kVStages) & 1);
                 tc_fence_after();
                 if (leader) {
 #pragma unroll
                     for (int kk = 0; kk < D / 16; ++kk) {
                         const uint32_t o16 = ((kk >> 2) * L::kSlab + (kk & 3) * 32) >> 4;
-                        umma_ss(tm + dqt::kDP, desc_make(do_lo + o16, kDescHiK), desc_make(kv_lo + sv_ * kTile16 + o16, kDescHiK),
+                        umma_ss(tm + dqt::kDP, desc_make(do_lo + o16, kDescHiK), desc_make(v_lo + sv_ * kTile16 + o16, kDescHiK),
                                 idesc_s, kk > 0);
                     }
                     tc_commit(bar_s_full);
+                    tc_commit(&bar_v_empty[sv_]);      // V_j is dead once dP_j has retired
                 }
             };
             mbar_wait(bar_q, 0);
@@ -188,21 +196,24 @@ flash_bwd_dq_kernel_sm100(const __grid_constant__ CUtensorMap tmQ, const __grid_
                 if (j + 1 < nb) {
                     mbar_wait(bar_s_empty, j & 1);
                     tc_fence_after();
+                    if (lane == 0) FA_BTRACE(1, j, 0);
                     issue_sdp(j + 1);
+                    if (lane == 0) FA_BTRACE(1, j, 1);
                 }
                 mbar_wait(bar_ds_full, j & 1);
                 tc_fence_after();
+                if (lane == 0) FA_BTRACE(1, j, 2);
                 if (leader) {
-                    const uint32_t ka = kvmn_lo + ((2 * j) % L::kSlots) * kTile16;
+                    const uint32_t ka = kmn_lo + (j % L::kKStages) * kTile16;
 #pragma unroll
                     for (int kk = 0; kk < kBM / 16; ++kk)
                         umma_ts(tm + dqt::kDQ, tm + dqt::kDS + kk * 8, desc_make(ka + kk * (2048 >> 4), kDescHiK), idesc_dq,
                                 (j > 0 || kk > 0));
                     tc_commit(bar_ds_empty);
-                    tc_commit(&bar_kv_empty[(2 * j) % L::kSlots]);
-                    tc_commit(&bar_kv_empty[(2 * j + 1) % L::kSlots]);
+                    tc_commit(&bar_k_empty[j % L::kKStages]);
                     if (j + 1 == nb) tc_commit(bar_dq_full);
                 }
+                if (lane == 0) FA_BTRACE(1, j, 3);
                 __syncwarp();
             }
         }
@@ -230,6 +241,7 @@ flash_bwd_dq_kernel_sm100(const __grid_constant__ CUtensorMap tmQ, const __grid_
             const int n0 = j * kBM;
             mbar_wait(bar_s_full, j & 1);
             tc_fence_after();
+            if (tid == 0) FA_BTRACE(0, j, 0);
             float s[64], dp[64];
             tmem_ld32(tS, *reinterpret_cast<uint32_t(*)[32]>(&s[0]));
             tmem_ld32(tS + 32, *reinterpret_cast<uint32_t(*)[32]>(&s[32]));
@@ -238,6 +250,7 @@ flash_bwd_dq_kernel_sm100(const __grid_constant__ CUtensorMap tmQ, const __grid_
             tmem_wait_ld();
             tc_fence_before();
             mbar_arrive(bar_s_empty);
+            if (tid == 0) FA_BTRACE(0, j, 1);
 
             const bool need_mask = (n0 + kBM > sg.sk_b) || (p.is_causal && (n0 + kBM - 1 > m0 + off));
             if (need_mask) {
@@ -254,11 +267,14 @@ flash_bwd_dq_kernel_sm100(const __grid_constant__ CUtensorMap tmQ, const __grid_
                 const float2 ds = __fmul2_rn(pr, __fadd2_rn(make_float2(dp[2 * i], dp[2 * i + 1]), ndv));
                 pk[i] = pack2<kBf16>(ds.x, ds.y);
             }
+            if (tid == 0) FA_BTRACE(0, j, 2);
             if (j > 0) mbar_wait(bar_ds_empty, (j - 1) & 1);
+            if (tid == 0) FA_BTRACE(0, j, 3);
             tmem_st32(tDS, pk);
             tmem_wait_st();
             tc_fence_before();
             mbar_arrive(bar_ds_full);
+            if (tid == 0) FA_BTRACE(0, j, 4);
         }
 
         // ---- epilogue: dQ * scale -> 16 bit -> smem (dead Q tile) -> coalesced stores ----
@@ -312,7 +328,7 @@ template <int D> struct DkvSmem {
     static constexpr int kTile = kBM * D * 2;
     static constexpr int kSubSlab = kSubQ * 128;       // 64-column slab of a 64-row Q/dO sub-tile (8 KB)
     static constexpr int kSub = kSubQ * D * 2;
-    static constexpr int kStages = 3;                  // each stage: Q sub-tile + dO sub-tile
+    static constexpr int kStages = 4;                  // each stage: Q sub-tile + dO sub-tile (TMA runs ~2 steps ahead)
     static constexpr int kOffK = 0;
     static constexpr int kOffV = kTile;
     static constexpr int kOffQdO = 2 * kTile;
@@ -366,14 +382,16 @@ flash_bwd_dk_dv_kernel_sm100(const __grid_constant__ CUtensorMap tmQ, const __gr
     float* sStat = reinterpret_cast<float*>(smem + L::kOffStat);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::kOffBar);
     uint64_t* bar_kv = bars;              // K + V landed
-    uint64_t* bar_qdo_full = bars + 1;    // [3]
-    uint64_t* bar_qdo_empty = bars + 4;   // [3]
-    uint64_t* bar_s_full = bars + 7;
-    uint64_t* bar_s_empty = bars + 8;     // 256
-    uint64_t* bar_p_full = bars + 9;      // 256
-    uint64_t* bar_p_empty = bars + 10;
-    uint64_t* bar_acc_full = bars + 11;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+    uint64_t* bar_qdo_full = bars + 1;                   // [kStages]
+    uint64_t* bar_qdo_empty = bars + 1 + L::kStages;     // [kStages]
+    uint64_t* bar_s_full = bars + 1 + 2 * L::kStages;
+    uint64_t* bar_s_empty = bar_s_full + 1;     // 256
+    uint64_t* bar_p_full = bar_s_full + 2;      // 256
+    uint64_t* bar_p_empty = bar_s_full + 3;
+    uint64_t* bar_acc_full = bar_s_full + 4;
+    uint64_t* bar_stat_full = bar_s_full + 5;   // [2] 64 arrivals (warps 10-11 published the column statistics)
+    uint64_t* bar_stat_empty = bar_s_full + 7;  // [2] 256 arrivals (every elementwise thread has them in registers)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_s_full + 9);
 
     if (warp == 8) {
         if (lane == 0) {
@@ -382,6 +400,7 @@ flash_bwd_dk_dv_kernel_sm100(const __grid_constant__ CUtensorMap tmQ, const __gr
             mbar_init(bar_s_full, 1); mbar_init(bar_s_empty, 256);
             mbar_init(bar_p_full, 256); mbar_init(bar_p_empty, 1);
             mbar_init(bar_acc_full, 1);
+            for (int i = 0; i < 2; ++i) { mbar_init(&bar_stat_full[i], kSubQ); mbar_init(&bar_stat_empty[i], 256); }
             fence_barrier_init();
         }
         __syncwarp();
@@ -435,16 +454,12 @@ flash_bwd_dk_dv_kernel_sm100(const __grid_constant__ CUtensorMap tmQ, const __gr
                 tc_fence_after();
                 if (leader) {
                     const uint32_t qa = qk_lo + stage * kStage16, da = qa + kSub16;
+                    // S^T = K Q^T and dP^T = V dO^T, interleaved: two independent accumulation chains in flight
 #pragma unroll
-                    for (int kk = 0; kk < D / 16; ++kk) {   // S^T = K Q^T
+                    for (int kk = 0; kk < D / 16; ++kk) {
                         const uint32_t oa = ((kk >> 2) * L::kSlab + (kk & 3) * 32) >> 4;
                         const uint32_t ob = ((kk >> 2) * L::kSubSlab + (kk & 3) * 32) >> 4;
                         umma_ss(tm + kvt::kSt, desc_make(k_lo + oa, kDescHiK), desc_make(qa + ob, kDescHiK), idesc_st, kk > 0);
-                    }
-#pragma unroll
-                    for (int kk = 0; kk < D / 16; ++kk) {   // dP^T = V dO^T
-                        const uint32_t oa = ((kk >> 2) * L::kSlab + (kk & 3) * 32) >> 4;
-                        const uint32_t ob = ((kk >> 2) * L::kSubSlab + (kk & 3) * 32) >> 4;
                         umma_ss(tm + kvt::kDPt, desc_make(v_lo + oa, kDescHiK), desc_make(da + ob, kDescHiK), idesc_st, kk > 0);
                     }
                     tc_commit(bar_s_full);
@@ -456,25 +471,53 @@ flash_bwd_dk_dv_kernel_sm100(const __grid_constant__ CUtensorMap tmQ, const __gr
                 if (st + 1 < tot) {
                     mbar_wait(bar_s_empty, st & 1);
                     tc_fence_after();
+                    if (lane == 0) FA_BTRACE(1, st, 0);
                     issue_sdp(st + 1);
+                    if (lane == 0) FA_BTRACE(1, st, 1);
                 }
                 mbar_wait(bar_p_full, st & 1);
                 tc_fence_after();
+                if (lane == 0) FA_BTRACE(1, st, 2);
                 if (leader) {
                     const uint32_t qa = qmn_lo + (st % L::kStages) * kStage16, da = qa + kSub16;
 #pragma unroll
-                    for (int kk = 0; kk < kSubQ / 16; ++kk)   // dV += P^T dO
+                    for (int kk = 0; kk < kSubQ / 16; ++kk) {  // dV += P^T dO and dK += dS^T Q, interleaved
                         umma_ts(tm + kvt::kDV, tm + kvt::kPt + kk * 8, desc_make(da + kk * (2048 >> 4), kDescHiK), idesc_acc,
                                 (st > 0 || kk > 0));
-#pragma unroll
-                    for (int kk = 0; kk < kSubQ / 16; ++kk)   // dK += dS^T Q
                         umma_ts(tm + kvt::kDK, tm + kvt::kDSt + kk * 8, desc_make(qa + kk * (2048 >> 4), kDescHiK), idesc_acc,
                                 (st > 0 || kk > 0));
+                    }
                     tc_commit(bar_p_empty);
                     tc_commit(&bar_qdo_empty[st % L::kStages]);
                     if (st + 1 == tot) tc_commit(bar_acc_full);
                 }
+                if (lane == 0) FA_BTRACE(1, st, 3);
                 __syncwarp();
+            }
+        } else {
+            // ===================== warps 10-11: column statistics loader =====================
+            // thread c of the 64 stages -LSE*log2e and -D of query row (sub-tile row c) for every step, two buffers ahead
+            const int c = tid - 320;
+            auto fetch = [&](int st, float& lse_raw, float& d_raw, bool& ok) {   // issue the two global loads, no use yet
+                const int hq = bidh_k * p.hratio + st / steps_per_head;
+                const int i = (it0 + st % steps_per_head) * kSubQ + c;
+                ok = i < sg.sq_b;
+                const int64_t o = ((int64_t)bidb * p.h + hq) * p.sq + (ok ? i : 0);
+                lse_raw = p.lse[o];
+                d_raw = p.dsum[o];
+            };
+            float lse_cur, d_cur, lse_nxt = 0.f, d_nxt = 0.f;
+            bool ok_cur, ok_nxt = false;
+            fetch(0, lse_cur, d_cur, ok_cur);
+            for (int st = 0; st < total; ++st) {
+                const int buf = st & 1;
+                if (st + 1 < total) fetch(st + 1, lse_nxt, d_nxt, ok_nxt);   // one step ahead: latency hidden behind the wait
+                mbar_wait(&bar_stat_empty[buf], ((st >> 1) & 1) ^ 1);
+                float* dst = sStat + buf * 2 * kSubQ;
+                dst[c] = ok_cur ? (-lse_cur * kLog2e) : -INFINITY;      // -inf => P = 0 for query rows beyond the sequence
+                dst[kSubQ + c] = ok_cur ? -d_cur : 0.f;
+                mbar_arrive(&bar_stat_full[buf]);
+                lse_cur = lse_nxt; d_cur = d_nxt; ok_cur = ok_nxt;
             }
         }
     } else {
@@ -491,39 +534,32 @@ flash_bwd_dk_dv_kernel_sm100(const __grid_constant__ CUtensorMap tmQ, const __gr
         const float c2 = p.scale * kLog2e;
         const float2 c2v = make_float2(c2, c2);
 
-        // per-column statistics of the current sub-tile, staged through shared memory by the first 64 threads
-        auto load_stats = [&](int st, float& nl, float& dd) {
-            const int hq = bidh_k * p.hratio + st / steps_per_head;
-            const int i = (it0 + st % steps_per_head) * kSubQ + tid;
-            if (i < sg.sq_b) {
-                const int64_t o = ((int64_t)bidb * p.h + hq) * p.sq + i;
-                nl = -p.lse[o] * kLog2e;
-                dd = -p.dsum[o];
-            } else {
-                nl = -INFINITY;   // P = 0 for query rows beyond the sequence
-                dd = 0.f;
-            }
-        };
-        float nl_next = 0.f, dd_next = 0.f;
-        if (tid < kSubQ) {
-            load_stats(0, nl_next, dd_next);
-            sStat[tid] = nl_next;
-            sStat[kSubQ + tid] = dd_next;
-        }
-        named_bar_sync(1, 256);
-
         for (int st = 0; st < total; ++st) {
             const int it = it0 + st % steps_per_head;
-            const float* stat = sStat + (st & 1) * 2 * kSubQ;
-            if (tid < kSubQ && st + 1 < total) load_stats(st + 1, nl_next, dd_next);   // prefetch (global loads in flight)
+            const int buf = st & 1;
             mbar_wait(bar_s_full, st & 1);
             tc_fence_after();
+            if (tid == 0) FA_BTRACE(0, st, 0);
             float s[32], dp[32];
             tmem_ld32(tSt, *reinterpret_cast<uint32_t(*)[32]>(&s[0]));
             tmem_ld32(tDPt, *reinterpret_cast<uint32_t(*)[32]>(&dp[0]));
             tmem_wait_ld();
             tc_fence_before();
-            mbar_arrive(bar_s_empty);
+            mbar_arrive(bar_s_empty);                // lets the MMA warp issue S^T/dP^T of the next step right away
+            // per-column statistics (-LSE*log2e, -D) of this sub-tile, staged by warps 10-11 (broadcast LDS.128).
+            // They are read AFTER the arrive on purpose: all the arithmetic below depends on them, which keeps the
+            // scheduler from sinking the TMEM loads / the arrive underneath the exponentials (measured: that delayed the
+            // next step's MMAs by ~700 cycles).
+            if (tid == 0) FA_BTRACE(0, st, 4);
+            mbar_wait(&bar_stat_full[buf], (st >> 1) & 1);
+            if (tid == 0) FA_BTRACE(0, st, 5);
+            const uint32_t stat = smem_u32(sStat) + (buf * 2 * kSubQ + g * 32) * 4;
+            float4 nl4[8], dd4[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                nl4[i] = lds128(stat + i * 16);
+                dd4[i] = lds128(stat + kSubQ * 4 + i * 16);
+            }
 
             // causal: key jg visible to query i iff jg <= i + off  <=>  column c >= jg - off - it*64 - 32 g
             const bool need_mask = p.is_causal && (it * kSubQ < n0 + kBM - 1 - off);
@@ -531,10 +567,8 @@ flash_bwd_dk_dv_kernel_sm100(const __grid_constant__ CUtensorMap tmQ, const __gr
             uint32_t pkp[16], pkd[16];
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
-                const float4 nl4 = *reinterpret_cast<const float4*>(stat + g * 32 + (i >> 1) * 4);          // broadcast
-                const float4 dd4 = *reinterpret_cast<const float4*>(stat + kSubQ + g * 32 + (i >> 1) * 4);
-                const float2 nl = (i & 1) ? make_float2(nl4.z, nl4.w) : make_float2(nl4.x, nl4.y);
-                const float2 dd = (i & 1) ? make_float2(dd4.z, dd4.w) : make_float2(dd4.x, dd4.y);
+                const float2 nl = (i & 1) ? make_float2(nl4[i >> 1].z, nl4[i >> 1].w) : make_float2(nl4[i >> 1].x, nl4[i >> 1].y);
+                const float2 dd = (i & 1) ? make_float2(dd4[i >> 1].z, dd4[i >> 1].w) : make_float2(dd4[i >> 1].x, dd4[i >> 1].y);
                 const float2 x = __ffma2_rn(make_float2(s[2 * i], s[2 * i + 1]), c2v, nl);
                 float2 pr = make_float2(fast_exp2(x.x), fast_exp2(x.y));
                 if (need_mask) {
@@ -545,19 +579,16 @@ flash_bwd_dk_dv_kernel_sm100(const __grid_constant__ CUtensorMap tmQ, const __gr
                 pkp[i] = pack2<kBf16>(pr.x, pr.y);
                 pkd[i] = pack2<kBf16>(ds.x, ds.y);
             }
+            if (tid == 0) FA_BTRACE(0, st, 1);
+            mbar_arrive(&bar_stat_empty[buf]);       // statistics consumed
             if (st > 0) mbar_wait(bar_p_empty, (st - 1) & 1);
+            if (tid == 0) FA_BTRACE(0, st, 2);
             tmem_st16(tPt, pkp);
             tmem_st16(tDSt, pkd);
             tmem_wait_st();
             tc_fence_before();
             mbar_arrive(bar_p_full);
-            // publish the next step's statistics (other buffer) and line the two warpgroups up
-            if (tid < kSubQ && st + 1 < total) {
-                float* nxt = sStat + ((st + 1) & 1) * 2 * kSubQ;
-                nxt[tid] = nl_next;
-                nxt[kSubQ + tid] = dd_next;
-            }
-            named_bar_sync(1, 256);
+            if (tid == 0) FA_BTRACE(0, st, 3);
         }
 
         // ---- epilogue: dV, dK * scale -> 16 bit -> smem (dead V / K tiles) -> coalesced stores ----
@@ -624,12 +655,54 @@ static int launch_tc(const BwdParams& kp, const CUtensorMap& tq128, const CUtens
     }
     if (kp.sq > 0) {
         dim3 g((kp.sq + kBM - 1) / kBM, kp.h, kp.b);
+#ifdef FA_TRACE
+        if (getenv("FA_B200_TRACE")) {
+            BwdParams kt = kp;
+            static long long* d_trace = nullptr;
+            if (!d_trace) cudaMalloc(&d_trace, 2 * 64 * 8 * sizeof(long long));
+            cudaMemsetAsync(d_trace, 0, 2 * 64 * 8 * sizeof(long long), stream);
+            kt.trace = d_trace;
+            kdq<<<g, 384, DqSmem<D>::kBytes, stream>>>(tq128, tdo128, tk, tv, kt);
+            cudaStreamSynchronize(stream);
+            static long long hh[2 * 64 * 8];
+            cudaMemcpy(hh, d_trace, sizeof(hh), cudaMemcpyDeviceToHost);
+            const long long t0 = hh[0];
+            for (int r = 0; r < 2; ++r)
+                for (int j = 0; j < 10; ++j) {
+                    printf("BTRACE dq %d %2d :", r, j);
+                    for (int e = 0; e < 5; ++e) printf(" %8lld", hh[(r * 64 + j) * 8 + e] ? hh[(r * 64 + j) * 8 + e] - t0 : -1LL);
+                    printf("\n");
+                }
+            fflush(stdout);
+        } else
+#endif
         kdq<<<g, 384, DqSmem<D>::kBytes, stream>>>(tq128, tdo128, tk, tv, kp);
         FA_CUDA_CHECK(cudaGetLastError());
         count_launch();
     }
     if (kp.sk > 0) {
         dim3 g((kp.sk + kBM - 1) / kBM, kp.h_k, kp.b);
+#ifdef FA_TRACE
+        if (getenv("FA_B200_TRACE")) {
+            BwdParams kt = kp;
+            static long long* d_trace2 = nullptr;
+            if (!d_trace2) cudaMalloc(&d_trace2, 2 * 64 * 8 * sizeof(long long));
+            cudaMemsetAsync(d_trace2, 0, 2 * 64 * 8 * sizeof(long long), stream);
+            kt.trace = d_trace2;
+            kkv<<<g, 384, DkvSmem<D>::kBytes, stream>>>(tq64, tdo64, tk, tv, kt);
+            cudaStreamSynchronize(stream);
+            static long long hh[2 * 64 * 8];
+            cudaMemcpy(hh, d_trace2, sizeof(hh), cudaMemcpyDeviceToHost);
+            const long long t0 = hh[0];
+            for (int r = 0; r < 2; ++r)
+                for (int j = 0; j < 10; ++j) {
+                    printf("BTRACE dkdv %d %2d :", r, j);
+                    for (int e = 0; e < 6; ++e) printf(" %8lld", hh[(r * 64 + j) * 8 + e] ? hh[(r * 64 + j) * 8 + e] - t0 : -1LL);
+                    printf("\n");
+                }
+            fflush(stdout);
+        } else
+#endif
         kkv<<<g, 384, DkvSmem<D>::kBytes, stream>>>(tq64, tdo64, tk, tv, kp);
         FA_CUDA_CHECK(cudaGetLastError());
         count_launch();

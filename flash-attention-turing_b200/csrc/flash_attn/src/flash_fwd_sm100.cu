@@ -592,54 +592,37 @@ flash_fwd_kernel_sm100(const __grid_constant__ CUtensorMap tmQ, const __grid_con
                     for (int c = 0; c < kBlockN; ++c)
                         if (c > lim) s[c] = -INFINITY;
                 }
-                // row max: 4 independent chains of 3-input max (FMNMX3)
-                float mxa = fmaxf(s[0], s[1]), mxb = fmaxf(s[2], s[3]), mxc = fmaxf(s[4], s[5]), mxd = fmaxf(s[6], s[7]);
+                // ---- online softmax with SPECULATIVE exponentials ----------------------------------------------
+                // The reference max m_ref only moves when the tile max exceeds it by more than 2^8 (lazy rescale), so
+                // for every tile but the first the exponentials can start immediately with the old reference while the
+                // row max (3-input FMNMX on the ALU pipe) is computed underneath the MUFU-bound exp loop.  Only if the
+                // vote afterwards says "rescale" (rare) is the first half recomputed with the new reference — the
+                // values are bit-identical to computing the max first, the critical path is ~350 cycles shorter.
+                if (j == 0) {   // no reference yet: exact max first
+                    float mxa = fmaxf(s[0], s[1]), mxb = fmaxf(s[2], s[3]), mxc = fmaxf(s[4], s[5]), mxd = fmaxf(s[6], s[7]);
 #pragma unroll
-                for (int c = 8; c < kBlockN; c += 8) {
-                    mxa = fmaxf(mxa, fmaxf(s[c], s[c + 1]));
-                    mxb = fmaxf(mxb, fmaxf(s[c + 2], s[c + 3]));
-                    mxc = fmaxf(mxc, fmaxf(s[c + 4], s[c + 5]));
-                    mxd = fmaxf(mxd, fmaxf(s[c + 6], s[c + 7]));
-                }
-                const float mx = fmaxf(fmaxf(mxa, mxb), fmaxf(mxc, mxd));
-                if (j == 0) {
-                    m_ref = mx;
-                } else {
-                    // lazy rescale: only when the max moved by more than 2^8
-                    const bool need = (mx - m_ref) * c2 > kRescaleThreshold;
-                    if (__any_sync(0xffffffffu, need)) {
-                        float alpha = 1.f;
-                        if (need) {
-                            alpha = fast_exp2((m_ref - mx) * c2);
-                            m_ref = mx;
-                            l_run *= alpha;
-                        }
-#pragma unroll
-                        for (int c = 0; c < D / 32; ++c) {
-                            uint32_t o[32];
-                            tmem_ld32(tO + c * 32, o);
-                            tmem_wait_ld();
-#pragma unroll
-                            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-                            tmem_st32(tO + c * 32, o);
-                        }
+                    for (int c = 8; c < kBlockN; c += 8) {
+                        mxa = fmaxf(mxa, fmaxf(s[c], s[c + 1]));
+                        mxb = fmaxf(mxb, fmaxf(s[c + 2], s[c + 3]));
+                        mxc = fmaxf(mxc, fmaxf(s[c + 4], s[c + 5]));
+                        mxd = fmaxf(mxd, fmaxf(s[c + 6], s[c + 7]));
                     }
+                    m_ref = fmaxf(fmaxf(mxa, mxb), fmaxf(mxc, mxd));
                 }
-                const float neg = (m_ref == -INFINITY) ? 0.f : -m_ref * c2;
+                float neg = (m_ref == -INFINITY) ? 0.f : -m_ref * c2;
                 if (r_in_tile == 0) FA_TRACE_EVENT(t, j, 2);
-                // P = 2^(s*c2 + neg).  kEmu of every 4 elements are evaluated on the FMA pipe (Cody-Waite split +
-                // degree-3 minimax polynomial, |rel err| < 7.5e-5, far below the 16-bit rounding of P) instead of the
-                // 16-per-clock MUFU.EX2 unit, which otherwise is as loaded as the tensor pipe at d=128.
-                const float s_floor = (-125.f - neg) * p.inv_scale_log2;  // clamp so that 2^x stays a normal float
-                const float2 c2v = make_float2(c2, c2), negv = make_float2(neg, neg);
+                const float2 c2v = make_float2(c2, c2);
                 const float2 magic = make_float2(12582912.f, 12582912.f);       // 1.5 * 2^23
-                float2 sum = make_float2(0.f, 0.f);
-                // two neighbouring columns at a time on the packed fp32x2 pipe (FFMA2 / FADD2)
-                auto ex2_pair = [&](float a, float b, bool emulate) -> float2 {
+                // P = 2^(s*c2 + neg), two neighbouring columns at a time on the packed fp32x2 pipe (FFMA2 / FADD2).
+                // kEmu of every 4 pairs use a Cody-Waite split + degree-3 minimax polynomial (|rel err| < 7.5e-5, far
+                // below the 16-bit rounding of P) on the FMA pipe instead of MUFU.EX2.
+                auto ex2_pair = [&](float a, float b, float negx, bool emulate) -> float2 {
+                    const float2 negv = make_float2(negx, negx);
                     if (!emulate) {
                         const float2 x = __ffma2_rn(make_float2(a, b), c2v, negv);
                         return make_float2(fast_exp2(x.x), fast_exp2(x.y));
                     }
+                    const float s_floor = (-125.f - negx) * p.inv_scale_log2;  // clamp so that 2^x stays a normal float
                     const float2 x = __ffma2_rn(make_float2(fmaxf(a, s_floor), fmaxf(b, s_floor)), c2v, negv);
                     const float2 tt = __fadd2_rn(x, magic);                   // low mantissa bits = rint(x)
                     const float2 nnf = __ffma2_rn(tt, make_float2(-1.f, -1.f), magic);   // -rint(x), exact
@@ -651,24 +634,75 @@ flash_fwd_kernel_sm100(const __grid_constant__ CUtensorMap tmQ, const __grid_con
                     return make_float2(__uint_as_float(__float_as_uint(pl.x) + (__float_as_uint(tt.x) << 23)),
                                        __uint_as_float(__float_as_uint(pl.y) + (__float_as_uint(tt.y) << 23)));
                 };
+
+                // first half of the columns, with the max of ALL 128 columns folded into the same loop
+                uint32_t pk0[32];
+                float2 sum_a = make_float2(0.f, 0.f);
+                float mxa = -INFINITY, mxb = -INFINITY, mxc = -INFINITY, mxd = -INFINITY;
 #pragma unroll
-                for (int half = 0; half < 2; ++half) {
-                    uint32_t pk[32];
+                for (int i = 0; i < 32; ++i) {
+                    const float2 pp = ex2_pair(s[2 * i], s[2 * i + 1], neg, (i & 3) < kEmu);
+                    sum_a = __fadd2_rn(sum_a, pp);
+                    pk0[i] = pack2<kBf16>(pp.x, pp.y);
+                    if ((i & 3) == 0) mxa = fmaxf(mxa, fmaxf(s[4 * i], s[4 * i + 1]));
+                    if ((i & 3) == 0) mxb = fmaxf(mxb, fmaxf(s[4 * i + 2], s[4 * i + 3]));
+                    if ((i & 3) == 1) mxc = fmaxf(mxc, fmaxf(s[4 * i], s[4 * i + 1]));
+                    if ((i & 3) == 1) mxd = fmaxf(mxd, fmaxf(s[4 * i + 2], s[4 * i + 3]));
+                    if ((i & 3) == 2) mxa = fmaxf(mxa, fmaxf(s[4 * i], s[4 * i + 1]));
+                    if ((i & 3) == 2) mxb = fmaxf(mxb, fmaxf(s[4 * i + 2], s[4 * i + 3]));
+                    if ((i & 3) == 3) mxc = fmaxf(mxc, fmaxf(s[4 * i], s[4 * i + 1]));
+                    if ((i & 3) == 3) mxd = fmaxf(mxd, fmaxf(s[4 * i + 2], s[4 * i + 3]));
+                }
+                {
+                    const float mx = fmaxf(fmaxf(mxa, mxb), fmaxf(mxc, mxd));
+                    const bool need = (mx - m_ref) * c2 > kRescaleThreshold;   // moved by more than 2^8 (never at j == 0)
+                    if (__any_sync(0xffffffffu, need)) {
+                        // slow path: rescale O_t and the running sum, redo the first half with the new reference
+                        float alpha = 1.f;
+                        if (need) {
+                            alpha = fast_exp2((m_ref - mx) * c2);
+                            m_ref = mx;
+                            l_run *= alpha;
+                            neg = -m_ref * c2;
+                        }
+#pragma unroll
+                        for (int c = 0; c < D / 32; ++c) {
+                            uint32_t o[32];
+                            tmem_ld32(tO + c * 32, o);
+                            tmem_wait_ld();
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+                            tmem_st32(tO + c * 32, o);
+                        }
+                        sum_a = make_float2(0.f, 0.f);
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) {
+                            const float2 pp = ex2_pair(s[2 * i], s[2 * i + 1], neg, (i & 3) < kEmu);
+                            sum_a = __fadd2_rn(sum_a, pp);
+                            pk0[i] = pack2<kBf16>(pp.x, pp.y);
+                        }
+                    }
+                }
+                tmem_st32(tS, pk0);
+                tmem_wait_st();
+                tc_fence_before();
+                mbar_arrive(&bar_p_full[2 * t]);
+                // second half
+                {
+                    uint32_t pk1[32];
 #pragma unroll
                     for (int i = 0; i < 32; ++i) {
-                        const int c = half * 64 + 2 * i;
-                        const float2 pp = ex2_pair(s[c], s[c + 1], (i & 3) < kEmu);
-                        sum = __fadd2_rn(sum, pp);
-                        pk[i] = pack2<kBf16>(pp.x, pp.y);
+                        const float2 pp = ex2_pair(s[64 + 2 * i], s[64 + 2 * i + 1], neg, (i & 3) < kEmu);
+                        sum_a = __fadd2_rn(sum_a, pp);
+                        pk1[i] = pack2<kBf16>(pp.x, pp.y);
                     }
-                    if (half == 1 && r_in_tile == 0) FA_TRACE_EVENT(t, j, 3);
-                    tmem_st32(tS + half * 32, pk);
+                    if (r_in_tile == 0) FA_TRACE_EVENT(t, j, 3);
+                    tmem_st32(tS + 32, pk1);
                     tmem_wait_st();
                     tc_fence_before();
-                    mbar_arrive(&bar_p_full[2 * t + half]);
+                    mbar_arrive(&bar_p_full[2 * t + 1]);
                 }
-                const float sum0 = sum.x, sum1 = sum.y;
-                l_run += sum0 + sum1;
+                l_run += sum_a.x + sum_a.y;
                 if (r_in_tile == 0) FA_TRACE_EVENT(t, j, 4);
             }
 
@@ -758,8 +792,8 @@ static int fwd_emu() {
     static int v = -1;
     if (v < 0) {
         const char* e = getenv("FA_B200_EMU");
-        v = e ? atoi(e) : 0;
-        if (v < 0 || v > 2) v = 0;
+        v = e ? atoi(e) : 1;   // measured best on B200: 1 of 4 pairs (+1.4 .. 2.4 %)
+        if (v < 0 || v > 2) v = 1;
     }
     return v;
 }

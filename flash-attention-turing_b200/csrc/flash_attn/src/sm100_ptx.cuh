@@ -252,6 +252,25 @@ FA_DEVICE void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// explicit shared-space accesses (the dynamic smem pointer goes through integer alignment arithmetic, after which the
+// compiler only knows a generic address and would emit LD.E / ST.E through the generic path)
+// ------------------------------------------------------------------------------------------------
+FA_DEVICE float4 lds128(uint32_t saddr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr));
+    return v;
+}
+FA_DEVICE uint4 lds128u(uint32_t saddr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(saddr));
+    return v;
+}
+FA_DEVICE void sts128u(uint32_t saddr, uint4 v) {
+    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+FA_DEVICE void sts32f(uint32_t saddr, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(saddr), "f"(v) : "memory"); }
+
+// ------------------------------------------------------------------------------------------------
 // math
 // ------------------------------------------------------------------------------------------------
 FA_DEVICE float fast_exp2(float x) {
