@@ -28,6 +28,12 @@ import threading
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
+try:  # torchrun exports OMP_NUM_THREADS=1; the CPU baseline legs must use every host core this process may run on
+    _NCORES = len(os.sched_getaffinity(0))
+except AttributeError:
+    _NCORES = os.cpu_count() or 1
+if int(os.environ.get("RANK", "0")) == 0:
+    os.environ["OMP_NUM_THREADS"] = str(_NCORES)
 sys.path.insert(0, os.path.join(ROOT, "flash-attention-turing_b200"))
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 sys.path.insert(0, ROOT)
@@ -117,6 +123,7 @@ def cpu_sdpa_baseline(s, d, causal, budget_s=12.0):
     import torch.nn.functional as F
     from torch.nn.attention import SDPBackend, sdpa_kernel
     heads = 4
+    torch.set_num_threads(_NCORES)
     torch.manual_seed(0)
     q, k, v = (torch.randn(1, heads, s, d) for _ in range(3))
     fl = fwd_flops(1, s, heads, d, causal)
@@ -156,6 +163,7 @@ def main():
     ap.add_argument("--config", default="C2", choices=list(CONFIGS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--bwd", action="store_true", help="also time the backward (dot + dQ + dK/dV kernels) and report it under \"bwd\"")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -237,6 +245,29 @@ def main():
     flops_rank = fwd_flops(b, s, h, d, causal)
     value = flops_rank * world / (ms_per_step * 1e-3) / 1e12
 
+    # ---- optional: backward leg (BASELINE config 4 is fwd+bwd); reported beside the headline, not inside it ----
+    bwd = None
+    if args.bwd:
+        do = torch.randn_like(q)
+        n_b = max(3, min(args.steps, 10))
+        for _ in range(2):
+            g = fat.bwd(q, k, v, o, lse, do, causal)
+        bwd_launches = fat.last_launch_count()
+        sync_all()
+        e0.record(stream)
+        for _ in range(n_b):
+            fat.bwd(q, k, v, o, lse, do, causal)
+        e1.record(stream)
+        sync_all()
+        tb = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(tb, op=dist.ReduceOp.MAX)
+        ms_b = float(tb.item()) / n_b
+        bwd = {"ms_per_step": ms_b, "value": 2.5 * flops_rank * world / (ms_b * 1e-3) / 1e12, "unit": "TFLOP/s (algorithmic 2.5x fwd)",
+               "steps": n_b, "gpu_launches_per_step": bwd_launches,
+               "kernels": "flash_bwd_dot_do_o_kernel_sm100 + flash_bwd_dq_kernel_sm100 + flash_bwd_dk_dv_kernel_sm100"}
+        del do, g
+
     # ---- end to end through the public API with host buffers ----
     e2e = None
     if not args.no_e2e:
@@ -293,6 +324,8 @@ def main():
         }
         if e2e:
             line["e2e"] = e2e
+        if bwd:
+            line["bwd"] = bwd
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_sdpa_baseline(s, d, causal)
         print(json.dumps(line), flush=True)

@@ -1,0 +1,49 @@
+"""benchmark.sh-compatible sweep (reference: /root/reference/benchmark.sh:17-45): for every (seqlen, head_dim, causal) of
+the reference's grid run fwd+bwd at batch 4, 16 heads and print a text table (the reference pipes ncu CSVs into
+matplotlib, which this image does not have; kernel times here come from CUDA events around each operator call).
+
+    python scripts/benchmark_sweep.py [--dtype fp16|bf16] [--quick]      (GPU box)
+"""
+import argparse, os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "flash-attention-turing_b200"))
+import torch
+import torch.nn.functional as F
+import flash_attn_turing as fat
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--dtype", default="fp16")
+ap.add_argument("--quick", action="store_true")
+args = ap.parse_args()
+dt = torch.float16 if args.dtype == "fp16" else torch.bfloat16
+batch_size, num_heads = 4, 16                                          # benchmark.sh:17-19
+seqlens = [512, 1024, 2048, 4096, 8192, 16384, 500, 1000, 2000, 4000, 8000, 16000]   # benchmark.sh:21
+if args.quick:
+    seqlens = [512, 4096, 4000]
+
+
+def timeit(fn, n):
+    for _ in range(2): fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(n): fn()
+    e1.record(); torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / n
+
+
+print(f"| seqlen | hdim | causal | flash_fwd_kernel ms | TFLOP/s | flash_bwd (dot+dq+dk_dv) ms | TFLOP/s | torch SDPA fwd ms | speed-up vs SDPA |")
+print("|---|---|---|---|---|---|---|---|---|")
+for s in seqlens:
+    for d in (64, 128):
+        for causal in (False, True):
+            torch.manual_seed(0)
+            q = torch.randn(batch_size, s, num_heads, d, device="cuda", dtype=dt); k = torch.randn_like(q); v = torch.randn_like(q); do = torch.randn_like(q)
+            n = 20 if s <= 4096 else 5
+            o, l = fat.fwd(q, k, v, causal)
+            tf = timeit(lambda: fat.fwd(q, k, v, causal), n)
+            tb = timeit(lambda: fat.bwd(q, k, v, o, l, do, causal), max(2, n // 2))
+            qt, kt, vt = [t.transpose(1, 2) for t in (q, k, v)]
+            ts = timeit(lambda: F.scaled_dot_product_attention(qt, kt, vt, is_causal=causal), n)
+            fl = 4 * batch_size * num_heads * s * s * d * (0.5 if causal else 1.0)
+            print(f"| {s} | {d} | {causal} | {tf:.3f} | {fl/tf/1e9:.0f} | {tb:.3f} | {2.5*fl/tb/1e9:.0f} | {ts:.3f} | {ts/tf:.2f}x |", flush=True)
