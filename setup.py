@@ -38,7 +38,7 @@ setup(
             library_dirs=[pkg_dir],
             libraries=["fa_b200", "c10_cuda", "torch_cuda"],
             runtime_library_dirs=["$ORIGIN"],
-            extra_compile_args=["-O2", "-std=c++17"],
+            extra_compile_args=["-O2", "-g0", "-std=c++17"],
         )
     ],
     install_requires=["torch"],
