@@ -15,6 +15,8 @@
 // ordered by decreasing cost (causal: later row blocks first) with the heads interleaved, and dealt round-robin to the
 // CTAs.  Every CTA therefore sees a sawtooth of costs that averages out (no atomics, deterministic), while the CTAs
 // that run concurrently work on the same few heads.
+#include <stdlib.h>
+
 #include "flash_fwd_common.cuh"
 
 namespace fa100 {
@@ -437,9 +439,15 @@ int launch_fwd_persistent(const fa_fwd_params* p, const CUtensorMap& tq, const C
     ts.num_mblk = (int)((p->seqlen_q + 2 * kBlockM - 1) / (2 * kBlockM));
     ts.bh = (int)(p->b * p->h);
     // (batch, head) pairs per group: their K and V (2 * sk * d * 2 bytes each pair of tensors... per KV head) should stay
-    // L2-resident while the group is being worked on; 48 MB of the 126 MB L2 is a comfortable share
+    // L2-resident while the group is being worked on (default 16 MB of the 126 MB L2, see FA_B200_GROUP_MB below)
     const int64_t kv_bytes_per_head = 2 * p->seqlen_k * p->d * 2;
-    int64_t grp = kv_bytes_per_head > 0 ? (48ll << 20) / kv_bytes_per_head : ts.bh;
+    static int64_t l2_budget_mb = -1;   // FA_B200_GROUP_MB: tuning knob for the L2 working set of one head group
+    if (l2_budget_mb < 0) {
+        const char* e = getenv("FA_B200_GROUP_MB");
+        l2_budget_mb = e ? atoll(e) : 16;   // measured on B200: 12-24 MB best (C2 and C3), 48+ loses L2 locality
+        if (l2_budget_mb < 1) l2_budget_mb = 1;
+    }
+    int64_t grp = kv_bytes_per_head > 0 ? (l2_budget_mb << 20) / kv_bytes_per_head : ts.bh;
     if (grp < 1) grp = 1;
     if (grp > ts.bh) grp = ts.bh;
     ts.group = (int)grp;
