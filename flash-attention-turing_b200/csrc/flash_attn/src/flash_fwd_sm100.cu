@@ -644,8 +644,10 @@ static int fwd_emu() {
     static int v = -1;
     if (v < 0) {
         const char* e = getenv("FA_B200_EMU");
-        v = e ? atoi(e) : 1;   // measured best on B200: 1 of 4 pairs (+1.4 .. 2.4 %)
-        if (v < 0 || v > 2) v = 1;
+        // measured on B200: 1 of 4 pairs is +1.4 % in a 20-launch burst but -0.5 % once the 1 kW power cap governs
+        // (300-launch loop), 2 of 4 is slower in both; default off
+        v = e ? atoi(e) : 0;
+        if (v < 0 || v > 2) v = 0;
     }
     return v;
 }
