@@ -1,5 +1,7 @@
 // flash_fwd_common.cuh — definitions shared by the forward kernels (flash_fwd_sm100.cu, flash_fwd_persist_sm100.cu).
 #pragma once
+#include <stdlib.h>
+
 #include "fa_common.h"
 #include "sm100_ptx.cuh"
 
@@ -162,9 +164,100 @@ FA_DEVICE void softmax_step(float (&s)[kBlockN], const bool first, const float c
     l_run += sum_a.x + sum_a.y;
 }
 
+// ---- persistent-kernel work list ----------------------------------------------------------------------
+struct TileSched {
+    int num_mblk;      // 256-row query blocks per (batch, head)
+    int bh;            // batch * heads
+    int group;         // (batch, head) pairs per L2 group
+    int total;         // num_mblk * bh
+};
+
+struct WorkItem {
+    int mblk, bidh, bidb;
+};
+
+FA_DEVICE WorkItem decode_item(const TileSched& ts, int n, int h, bool causal) {
+    const int per_group = ts.group * ts.num_mblk;
+    const int g = n / per_group;
+    int r = n - g * per_group;
+    const int heads_here = min(ts.group, ts.bh - g * ts.group);   // the last group may be smaller
+    const int level = r / heads_here;
+    const int head_local = r - level * heads_here;
+    const int bhi = g * ts.group + head_local;
+    WorkItem w;
+    w.mblk = causal ? (ts.num_mblk - 1 - level) : level;          // heaviest causal row blocks first
+    w.bidb = bhi / h;
+    w.bidh = bhi - w.bidb * h;
+    return w;
+}
+
+// geometry of one work item (identical in every role)
+struct ItemGeom {
+    int m0, q_row0, k_row0, sq_b, sk_b, tma_b, causal_off, nblk[2], n_blocks;
+    bool skip;
+};
+FA_DEVICE ItemGeom item_geom(const FwdParams& p, const WorkItem& w) {
+    ItemGeom g;
+    g.m0 = w.mblk * (2 * kBlockM);
+    if (p.cu_q != nullptr) {
+        g.q_row0 = p.cu_q[w.bidb];
+        g.sq_b = p.cu_q[w.bidb + 1] - g.q_row0;
+        g.k_row0 = p.cu_k[w.bidb];
+        g.sk_b = p.cu_k[w.bidb + 1] - g.k_row0;
+        g.tma_b = 0;
+    } else {
+        g.q_row0 = 0; g.k_row0 = 0; g.sq_b = p.sq; g.sk_b = p.sk; g.tma_b = w.bidb;
+    }
+    g.skip = g.m0 >= g.sq_b;
+    g.causal_off = g.sk_b - g.sq_b;
+#pragma unroll
+    for (int t = 0; t < 2; ++t) {
+        const int mt = g.m0 + t * kBlockM;
+        int kv_end = (mt < g.sq_b) ? g.sk_b : 0;
+        if (p.is_causal) kv_end = min(kv_end, max(0, mt + kBlockM + g.causal_off));
+        g.nblk[t] = (kv_end + kBlockN - 1) / kBlockN;
+    }
+    g.n_blocks = max(g.nblk[0], g.nblk[1]);
+    return g;
+}
+
+// shared memory of the persistent kernel = the non-persistent layout + one 16-bit O tile used as the source of the
+// TMA store (D = 128: 64 KB Q + 128 KB K/V ring + 32 KB staging = 224 KB, just inside the 227 KB limit)
+template <int D> struct FwdSmemP : FwdSmem<D> {
+    static constexpr int kOffStage = FwdSmem<D>::kOffKV + FwdSmem<D>::kKvStages * FwdSmem<D>::kTile;
+    static constexpr int kOffBarP = kOffStage + FwdSmem<D>::kTile;
+    static constexpr int kBytesP = kOffBarP + 512 + 1024;
+};
+
+// static work list of the persistent kernels (host side): see the comment at decode_item
+inline TileSched make_tile_sched(const fa_fwd_params* p) {
+    TileSched ts;
+    ts.num_mblk = (int)((p->seqlen_q + 2 * kBlockM - 1) / (2 * kBlockM));
+    ts.bh = (int)(p->b * p->h);
+    // (batch, head) pairs per group: their K and V (2 * sk * d * 2 bytes each pair of tensors... per KV head) should stay
+    // L2-resident while the group is being worked on (default 16 MB of the 126 MB L2, see FA_B200_GROUP_MB below)
+    const int64_t kv_bytes_per_head = 2 * p->seqlen_k * p->d * 2;
+    static int64_t l2_budget_mb = -1;   // FA_B200_GROUP_MB: tuning knob for the L2 working set of one head group
+    if (l2_budget_mb < 0) {
+        const char* e = getenv("FA_B200_GROUP_MB");
+        l2_budget_mb = e ? atoll(e) : 16;   // measured on B200: 12-24 MB best (C2 and C3), 48+ loses L2 locality
+        if (l2_budget_mb < 1) l2_budget_mb = 1;
+    }
+    int64_t grp = kv_bytes_per_head > 0 ? (l2_budget_mb << 20) / kv_bytes_per_head : ts.bh;
+    if (grp < 1) grp = 1;
+    if (grp > ts.bh) grp = ts.bh;
+    ts.group = (int)grp;
+    ts.total = ts.num_mblk * ts.bh;
+    return ts;
+}
+
 // launchers of the individual kernels (one translation unit each); return FA_OK / FA_ERR_*
 template <int D, bool kBf16, int kEmu>
 int launch_fwd_persistent(const fa_fwd_params* p, const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, FwdParams kp,
                           cudaStream_t stream);
+// head_dim 128 only: four softmax warpgroups (two per query tile, each thread owns half a score row)
+template <bool kBf16, int kEmu>
+int launch_fwd_p4(const fa_fwd_params* p, const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, FwdParams kp,
+                  cudaStream_t stream);
 
 }  // namespace fa100

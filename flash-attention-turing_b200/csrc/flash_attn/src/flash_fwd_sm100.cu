@@ -658,7 +658,7 @@ static int fwd_variant() {
     static int v = -1;
     if (v < 0) {
         const char* e = getenv("FA_B200_FWD");
-        v = (e && e[0] == 'g') ? 1 : (e && e[0] == 'n') ? 2 : 0;
+        v = (e && e[0] == 'g') ? 1 : (e && e[0] == 'n') ? 2 : (e && e[0] == 'p' && e[1] == '4') ? 3 : 0;
     }
     return v;
 }
@@ -717,7 +717,8 @@ int launch_fwd_sm100(const fa_fwd_params* p, cudaStream_t stream) {
     }
 #ifdef FA_TRACE
     if (do_trace && p->d == 128 && bf16) {
-        int rc = fwd_variant() == 0 ? launch_fwd_persistent<128, true, 1>(p, tq, tk, tv, kp, stream)
+        int rc = fwd_variant() == 3 ? (fwd_emu() == 1 ? launch_fwd_p4<true, 1>(p, tq, tk, tv, kp, stream) : launch_fwd_p4<true, 0>(p, tq, tk, tv, kp, stream))
+               : fwd_variant() == 0 ? launch_fwd_persistent<128, true, 1>(p, tq, tk, tv, kp, stream)
                                     : launch_fwd_ws<128, true, 1>(p, tq, tk, tv, kp, stream);
         cudaStreamSynchronize(stream);
         static long long h[3 * 64 * 8];
@@ -734,7 +735,14 @@ int launch_fwd_sm100(const fa_fwd_params* p, cudaStream_t stream) {
         return rc;
     }
 #endif
-    if (fwd_variant() == 0) {   // persistent kernel (flash_fwd_persist_sm100.cu)
+    if (fwd_variant() == 3 && p->d == 128) {   // four softmax warpgroups (flash_fwd_p4_sm100.cu)
+        switch (fwd_emu()) {
+            case 0: return bf16 ? launch_fwd_p4<true, 0>(p, tq, tk, tv, kp, stream) : launch_fwd_p4<false, 0>(p, tq, tk, tv, kp, stream);
+            case 1: return bf16 ? launch_fwd_p4<true, 1>(p, tq, tk, tv, kp, stream) : launch_fwd_p4<false, 1>(p, tq, tk, tv, kp, stream);
+            default: return bf16 ? launch_fwd_p4<true, 2>(p, tq, tk, tv, kp, stream) : launch_fwd_p4<false, 2>(p, tq, tk, tv, kp, stream);
+        }
+    }
+    if (fwd_variant() == 0 || fwd_variant() == 3) {   // persistent kernel (flash_fwd_persist_sm100.cu)
         if (p->d == 128) {
             switch (fwd_emu()) {
                 case 0: return bf16 ? launch_fwd_persistent<128, true, 0>(p, tq, tk, tv, kp, stream) : launch_fwd_persistent<128, false, 0>(p, tq, tk, tv, kp, stream);

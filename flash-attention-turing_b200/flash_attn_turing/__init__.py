@@ -67,5 +67,7 @@ def flash_attn_func(q, k, v, *legacy_dims, causal: bool = False):
 
 
 from . import sharded  # noqa: E402,F401  (batch-shard runner for multi-GPU boxes)
+from .hostio import HostForward, fwd_host  # noqa: E402,F401  (host-resident tensors: chunked copy/compute pipeline)
 
-__all__ = ["fwd", "bwd", "varlen_fwd", "varlen_bwd", "flash_attn_func", "last_launch_count", "LIB_PATH", "sharded"]
+__all__ = ["fwd", "bwd", "varlen_fwd", "varlen_bwd", "flash_attn_func", "last_launch_count", "LIB_PATH", "sharded",
+           "fwd_host", "HostForward"]

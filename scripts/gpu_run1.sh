@@ -1,0 +1,28 @@
+#!/bin/bash
+# GPU session 1 of the 4-softmax-warpgroup forward (p4): correctness, timing matrix, clock64 trace, test suite, bench
+set -u
+mkdir -p gpurun_out
+L=gpurun_out/run1.log
+exec > >(tee -a $L) 2>&1
+nvidia-smi --query-gpu=name,power.limit,clocks.max.sm,clocks.sm --format=csv
+echo "== p4 quick correctness"
+FA_B200_FWD=p4 timeout 300 python scripts/time_fwd.py S1k C2c C2 || echo "P4 QUICK FAILED rc=$?"
+echo "== timing matrix (burst)"
+FA_TIME_SDPA=1 timeout 300 python scripts/time_fwd.py C2 C3 C4
+for emu in 0 1 2; do
+  FA_B200_FWD=p4 FA_B200_EMU=$emu timeout 300 python scripts/time_fwd.py C2 C3 C4 || echo "P4 EMU $emu FAILED"
+done
+echo "== sustained (200 launches)"
+FA_ITERS=200 timeout 300 python scripts/time_fwd.py C2
+FA_ITERS=200 FA_B200_FWD=p4 timeout 300 python scripts/time_fwd.py C2
+FA_ITERS=200 FA_B200_FWD=p4 FA_B200_EMU=1 timeout 300 python scripts/time_fwd.py C2
+echo "== trace p4"
+LD_LIBRARY_PATH=flash-attention-turing_b200/build/trace FA_B200_FWD=p4 timeout 200 python scripts/trace_fwd.py > gpurun_out/trace_p4.log 2>&1; tail -45 gpurun_out/trace_p4.log
+echo "== pytest gpu with p4"
+FA_B200_FWD=p4 timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -15
+echo "== ubench"
+timeout 120 ./scripts/ubench_softmax.bin
+echo "== bench"
+timeout 600 python bench.py --bwd > gpurun_out/bench_default.json 2> gpurun_out/bench_default.err; cat gpurun_out/bench_default.json; tail -3 gpurun_out/bench_default.err
+FA_B200_FWD=p4 timeout 600 python bench.py --no-cpu-baseline > gpurun_out/bench_p4.json 2> gpurun_out/bench_p4.err; cat gpurun_out/bench_p4.json; tail -3 gpurun_out/bench_p4.err
+echo "== done"

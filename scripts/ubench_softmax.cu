@@ -16,6 +16,29 @@ __device__ __forceinline__ void row_tile(float (&s)[128], float c2, float neg, f
     for (int i = 0; i < 64; ++i) {
         float2 pp;
         const bool emulate = (i & 3) < kEmu;
+        if (kMode == 3) {  // two exponentials per MUFU instruction: ex2.approx.f16x2 on a packed half2 argument
+            const float2 x = __ffma2_rn(make_float2(s[2 * i], s[2 * i + 1]), c2v, negv);
+            uint32_t xh, ph;
+            asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(xh) : "f"(x.y), "f"(x.x));
+            asm("ex2.approx.f16x2 %0, %1;" : "=r"(ph) : "r"(xh));
+            float p0, p1;
+            asm("{.reg .b16 lo, hi; mov.b32 {lo, hi}, %2; cvt.f32.f16 %0, lo; cvt.f32.f16 %1, hi;}" : "=f"(p0), "=f"(p1) : "r"(ph));
+            pp = make_float2(p0, p1);
+            sum = __fadd2_rn(sum, pp);
+            pk[i] = pack_bf16(pp.x, pp.y);
+            continue;
+        }
+        if (kMode == 4) {  // as mode 3 but P stays fp16 (the fp16 kernel): no unpack for P, sum via f32 unpack
+            const float2 x = __ffma2_rn(make_float2(s[2 * i], s[2 * i + 1]), c2v, negv);
+            uint32_t xh, ph;
+            asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(xh) : "f"(x.y), "f"(x.x));
+            asm("ex2.approx.f16x2 %0, %1;" : "=r"(ph) : "r"(xh));
+            float p0, p1;
+            asm("{.reg .b16 lo, hi; mov.b32 {lo, hi}, %2; cvt.f32.f16 %0, lo; cvt.f32.f16 %1, hi;}" : "=f"(p0), "=f"(p1) : "r"(ph));
+            sum = __fadd2_rn(sum, make_float2(p0, p1));
+            pk[i] = ph;
+            continue;
+        }
         if (kMode == 1) {  // scalar math (FFMA/FADD) instead of packed
             const float x0 = fmaf(s[2 * i], c2, neg), x1 = fmaf(s[2 * i + 1], c2, neg);
             pp = make_float2(ex2f(x0), ex2f(x1));
@@ -42,7 +65,7 @@ __device__ __forceinline__ void row_tile(float (&s)[128], float c2, float neg, f
 }
 
 template <int kEmu, int kMode>
-__global__ void __launch_bounds__(256, 1) bench(float* out, long long* cycles, int iters, float c2) {
+__global__ void __launch_bounds__(512, 1) bench(float* out, long long* cycles, int iters, float c2) {
     float s[128];
 #pragma unroll
     for (int i = 0; i < 128; ++i) s[i] = -0.01f * (float)((threadIdx.x * 7 + i * 13) % 97);
@@ -71,7 +94,7 @@ __global__ void __launch_bounds__(256, 1) bench(float* out, long long* cycles, i
 
 template <int kEmu, int kMode> void run(const char* name, int threads) {
     float* out; long long* cyc;
-    cudaMalloc(&out, 148 * 256 * 4); cudaMalloc(&cyc, 148 * 8);
+    cudaMalloc(&out, 148 * 512 * 4); cudaMalloc(&cyc, 148 * 8);
     const int iters = 200;
     bench<kEmu, kMode><<<148, threads>>>(out, cyc, iters, 0.1275f);
     bench<kEmu, kMode><<<148, threads>>>(out, cyc, iters, 0.1275f);
@@ -84,7 +107,7 @@ template <int kEmu, int kMode> void run(const char* name, int threads) {
 }
 
 int main() {
-    for (int threads : {128, 256}) {
+    for (int threads : {128, 256, 512}) {
         run<0, 1>("scalar mufu", threads);
         run<0, 0>("packed mufu emu0", threads);
         run<1, 0>("packed emu1 (25%)", threads);
@@ -92,6 +115,8 @@ int main() {
         run<3, 0>("packed emu3 (75%)", threads);
         run<4, 0>("packed emu4 (100%)", threads);
         run<0, 2>("packed mufu + rowmax", threads);
+        run<0, 3>("ex2.f16x2 -> bf16 P", threads);
+        run<0, 4>("ex2.f16x2 -> fp16 P", threads);
     }
     return 0;
 }

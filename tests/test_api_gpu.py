@@ -75,6 +75,21 @@ def test_flash_attn_func_autograd(fat):
     assert_close(out_c, attention_ref(q.detach(), k.detach(), v.detach(), True)[0], dt, "out causal")
 
 
+@pytest.mark.parametrize("chunks", [None, 2, 3])
+def test_fwd_host_pipeline_is_bit_identical_to_fwd(fat, chunks):
+    """host-resident tensors through the chunked H2D / kernel / D2H pipeline == the device call, bit for bit"""
+    dt = torch.bfloat16
+    q, k, v, _ = _rand(5, 300, 333, 4, 2, 128, dt, seed=11)
+    o, l = fat.fwd(q, k, v, True)
+    hq, hk, hv = (t.cpu().pin_memory() for t in (q, k, v))
+    for _ in range(2):          # second call reuses the staging slots
+        ho, hl = fat.fwd_host(hq, hk, hv, True, chunks=chunks)
+        assert not ho.is_cuda and ho.dtype == dt and hl.shape == (5, 4, 300)
+        assert torch.equal(ho, o.cpu()) and torch.equal(hl, l.cpu())
+    with pytest.raises(ValueError):
+        fat.fwd_host(q, k, v, True)
+
+
 def test_error_behaviour_matches_reference_checks(fat):
     q, k, v, _ = _rand(1, 64, 64, 4, 2, 128, torch.float16)
     with pytest.raises(RuntimeError, match="rank-4"):

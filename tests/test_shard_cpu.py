@@ -53,6 +53,17 @@ def _free_port():
         return s.getsockname()[1]
 
 
+def test_host_pipeline_chunk_ranges():
+    from flash_attn_turing.hostio import chunk_ranges
+    assert chunk_ranges(4, 4) == [(0, 1), (1, 2), (2, 3), (3, 4)]
+    assert chunk_ranges(5, 2) == [(0, 3), (3, 5)]
+    assert chunk_ranges(2, 8) == [(0, 1), (1, 2)]
+    for b in range(0, 9):
+        for n in range(1, 6):
+            r = chunk_ranges(b, n)
+            assert sum(e - s for s, e in r) == b and all(e > s for s, e in r)
+
+
 def test_shard_ranges():
     sh = _load_sharded()
     assert sh.shard_ranges(256, 8) == [(32 * i, 32 * i + 32) for i in range(8)]
