@@ -9,8 +9,11 @@
 // warpgroups (columns [0,64) and [64,128)), so each tile's softmax always has two warps per sub-partition and the MUFU
 // pipe is saturated even when the tiles' phases do not overlap.
 //
-// Roles (640 threads): warpgroup 2t+hh = softmax of tile t, column half hh (112 registers/thread);
+// Roles (640 threads): warpgroup 2t+hh = softmax of tile t, column half hh (104 registers/thread);
 //                      warp 16 = MMA issuer, warp 17 = TMA producer (warpgroup 4, 64 registers/thread).
+// Register budget: five warps per SM sub-partition launch with 96 registers each; setmaxnreg.inc can only draw what
+// setmaxnreg.dec released (the launch-time slack of the register file is NOT in the pool: a 112/64 split deadlocks),
+// so warpgroup 4 gives up 32 per thread and each of the four softmax warps of a sub-partition takes 8.
 // TMEM plan is the one of the two-warpgroup kernel (S0 S1 O0 O1, 128 columns each); P_t half hh overwrites the first
 // 32 columns of ITS OWN half of S_t (columns 64hh .. 64hh+32), so a thread can re-read its scores from TMEM in the
 // rare rescale path and never has to keep them live in registers.
@@ -214,7 +217,7 @@ flash_fwd_kernel_sm100_p4(const __grid_constant__ CUtensorMap tmQ, const __grid_
         }
     } else {
         // ========== softmax warpgroups: warpgroup 2t+hh owns columns [64hh, 64hh+64) of tile slot t, one thread per row ==========
-        setmaxnreg_inc<112>();
+        setmaxnreg_inc<104>();
         const int t = wg >> 1;
         const int hh = wg & 1;
         const int wq = warp & 3;                         // TMEM lane quadrant = SM sub-partition
