@@ -3,7 +3,7 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config C2|C3|C4fwd|C5shard]
 
-A "step" is one forward pass (one launch of flash_fwd_kernel_sm100 through the C ABI) over one synthetic batch.
+A "step" is one forward pass (one launch of flash_fwd_kernel_sm100_p4 through the C ABI) over one synthetic batch.
 Default workload = BASELINE.json configs[1] ("C2": b4 s4096 h32 d128 bf16 forward, non-causal) on every rank; for
 N > 1 the (batch x head) problems are sharded by batch — each rank owns an independent b=4 slab, no collective on
 the data path — so scaling is "weak" and `value` = all ranks' FLOPs / max-over-ranks device time.
@@ -318,7 +318,7 @@ def main():
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peaks["burst"], "unit": "TFLOP/s",
                          "frac": achieved / peaks["burst"], "traffic": traffic, "peak_source": peaks["source"],
                          "frac_of_sustained": (achieved / peaks["sustained"]) if peaks["sustained"] else None,
-                         "frac_of_nominal_2250": achieved / 2250.0, "kernel": "flash_fwd_kernel_sm100<128,bf16>"},
+                         "frac_of_nominal_2250": achieved / 2250.0, "kernel": "flash_fwd_kernel_sm100_p4<bf16> (FA_B200_FWD / FA_B200_EMU select the A/B variants)"},
             "gpu_launches": launches_per_step * args.steps,
             "clocks": clocks,
         }

@@ -19,6 +19,12 @@
 // rare rescale path and never has to keep them live in registers.
 // The two threads of a row agree on the running reference max through a 4-byte shared-memory slot each and a
 // 64-thread named barrier per warp pair; the exponentials still start speculatively with the old reference.
+#include <type_traits>
+
+#ifndef FA_P4_SUMVOTE
+#define FA_P4_SUMVOTE 1   // 0: per-element row max + vote (A/B builds); 1: vote on the tile sum, max only when it trips
+#endif
+
 #include "flash_fwd_common.cuh"
 
 namespace fa100 {
@@ -27,8 +33,9 @@ namespace {
 constexpr int D = 128;
 constexpr int kThreadsP4 = 640;
 using L = FwdSmemP<D>;
-constexpr int kOffXch = L::kOffBarP + 256;            // float [2 tiles][2 halves][128 rows]
-constexpr int kNeedP4 = kOffXch + 2 * 2 * kBlockM * 4;
+constexpr int kOffXch = L::kOffBarP;                  // float [2 tiles][2 halves][128 rows], 1024-byte aligned: peer slot = own ^ 512
+constexpr int kOffBars = kOffXch + 2 * 2 * kBlockM * 4;
+constexpr int kNeedP4 = kOffBars + 256;
 constexpr int kBytesP4 = 232448;                      // everything an SM has (227 KB); the slack absorbs a base that is not 1024-byte aligned
 static_assert(kNeedP4 + 512 <= kBytesP4, "shared memory budget");
 }  // namespace
@@ -52,7 +59,7 @@ flash_fwd_kernel_sm100_p4(const __grid_constant__ CUtensorMap tmQ, const __grid_
     uint8_t* sQ = smem + L::kOffQ;
     uint8_t* sKV = smem + L::kOffKV;
     uint8_t* sStage = smem + L::kOffStage;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::kOffBarP);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kOffBars);
     uint64_t* bar_q_full = bars;                      // [2]  Q_t landed
     uint64_t* bar_q_empty = bars + 2;                 // [2]  last S_t MMA of the item retired
     uint64_t* bar_kv_full = bars + 4;                 // [kStages]
@@ -226,7 +233,6 @@ flash_fwd_kernel_sm100_p4(const __grid_constant__ CUtensorMap tmQ, const __grid_
         const uint32_t tS = tmem_base + lane_base + kTmemS0 + t * 128 + hh * 64;   // own scores; own P half goes to the same place
         const uint32_t tO = tmem_base + lane_base + kTmemO0 + t * 128 + hh * 64;   // own half of the O row
         const uint32_t x_own = xch + ((t * 2 + hh) * kBlockM + r_in_tile) * 4;
-        const uint32_t x_peer = xch + ((t * 2 + (hh ^ 1)) * kBlockM + r_in_tile) * 4;
         const uint32_t pair_bar = 1 + t * 4 + wq;       // named barriers 1..8: the two warps that share 32 rows (64 threads)
         const uint32_t tile_bar = 9 + t;                // named barriers 9, 10: the two warpgroups of a tile (256 threads)
         uint16_t* o_base = reinterpret_cast<uint16_t*>(p.o);
@@ -235,18 +241,22 @@ flash_fwd_kernel_sm100_p4(const __grid_constant__ CUtensorMap tmQ, const __grid_
         int its = 0;       // S_t steps so far
         int nitem = 0;     // items with keys finished by this slot
 
-        // P = 2^(s*c2 + neg) for this thread's 64 scores -> 32 packed words, returns the (unscaled) partial row sum.
-        // kEmu of every 4 column pairs go through the Cody-Waite + degree-3 polynomial path on the FMA pipe.
-        auto exp_half = [&](const float (&s)[64], const float neg, uint32_t (&pk)[32]) -> float {
+        // The 64 scores of a thread are walked in four chunks of 16 columns (tcgen05.ld x16), the next chunk in flight
+        // while the current one is processed: only 32 score registers are ever live next to the 32 packed P words, which
+        // is what lets this role fit 104 registers without local-memory traffic in the loop (L1 is ~0 KB here: shared
+        // memory takes all of it, a spill costs an L2 round trip).
+        // P = 2^(s*c2 + neg); kEmu of every 4 column pairs go through the Cody-Waite + degree-3 polynomial path (FMA pipe).
+        auto exp_chunk = [&](const float (&s)[16], const float neg, uint32_t* pk8, float2& sum) {
             const float2 c2v = make_float2(c2, c2);
             const float2 negv = make_float2(neg, neg);
-            const float2 magic = make_float2(12582912.f, 12582912.f);       // 1.5 * 2^23
-            const float s_floor = (-125.f - neg) * inv_c2;                  // keeps the emulated 2^x a normal float
-            float2 sum = make_float2(0.f, 0.f);
+            // kEmu -> emulated pairs of every 8 (spread evenly): 4 -> {0}, 1 -> {0,4}, 3 -> {0,3,6}, 2 -> {0,2,4,6}
+            constexpr int kEmu8 = kEmu == 1 ? 2 : kEmu == 2 ? 4 : kEmu == 3 ? 3 : kEmu == 4 ? 1 : 0;
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
+            for (int i = 0; i < 8; ++i) {
                 float2 pp;
-                if ((i & 3) < kEmu) {
+                if (((i * kEmu8) & 7) < kEmu8) {
+                    const float2 magic = make_float2(12582912.f, 12582912.f);       // 1.5 * 2^23
+                    const float s_floor = (-125.f - neg) * inv_c2;                  // keeps the emulated 2^x a normal float
                     const float2 x = __ffma2_rn(make_float2(fmaxf(s[2 * i], s_floor), fmaxf(s[2 * i + 1], s_floor)), c2v, negv);
                     const float2 tt = __fadd2_rn(x, magic);                                   // low mantissa bits = rint(x)
                     const float2 nnf = __ffma2_rn(tt, make_float2(-1.f, -1.f), magic);        // -rint(x), exact
@@ -262,19 +272,48 @@ flash_fwd_kernel_sm100_p4(const __grid_constant__ CUtensorMap tmQ, const __grid_
                     pp = make_float2(fast_exp2(x.x), fast_exp2(x.y));
                 }
                 sum = __fadd2_rn(sum, pp);
-                pk[i] = pack2<kBf16>(pp.x, pp.y);
+                pk8[i] = pack2<kBf16>(pp.x, pp.y);
             }
-            return sum.x + sum.y;
         };
-        auto load_scores = [&](float (&s)[64], const bool need_mask, const int lim) {
-            tmem_ld32(tS, *reinterpret_cast<uint32_t(*)[32]>(&s[0]));
-            tmem_ld32(tS + 32, *reinterpret_cast<uint32_t(*)[32]>(&s[32]));
-            tmem_wait_ld();
-            if (need_mask) {
+        auto mask_chunk = [&](float (&s)[16], const int lim_c) {
 #pragma unroll
-                for (int c = 0; c < 64; ++c)
-                    if (c > lim) s[c] = -INFINITY;
+            for (int c = 0; c < 16; ++c)
+                if (c > lim_c) s[c] = -INFINITY;
+        };
+        auto max_chunk = [&](const float (&s)[16], float mx) -> float {
+            float ma = fmaxf(s[0], s[1]), mb = fmaxf(s[2], s[3]);
+#pragma unroll
+            for (int c = 4; c < 16; c += 4) {
+                ma = fmaxf(ma, fmaxf(s[c], s[c + 1]));
+                mb = fmaxf(mb, fmaxf(s[c + 2], s[c + 3]));
             }
+            return fmaxf(mx, fmaxf(ma, mb));
+        };
+        // one pass over the thread's 64 scores: kExp -> exponentials into pk / sum; kMax -> running max into mx
+        auto walk_m = [&](auto do_exp, auto do_max, auto do_mask, const int lim, const float neg, uint32_t (&pk)[32],
+                          float2& sum, float& mx) {
+            float sa[16], sb[16];
+            tmem_ld16(tS, *reinterpret_cast<uint32_t(*)[16]>(&sa[0]));
+            tmem_wait_ld();
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                float (&cur)[16] = (c & 1) ? sb : sa;
+                float (&nxt)[16] = (c & 1) ? sa : sb;
+                if (c < 3) tmem_ld16(tS + 16 * (c + 1), *reinterpret_cast<uint32_t(*)[16]>(&nxt[0]));
+                if constexpr (decltype(do_mask)::value) mask_chunk(cur, lim - 16 * c);
+                if constexpr (decltype(do_max)::value) mx = max_chunk(cur, mx);
+                if constexpr (decltype(do_exp)::value) exp_chunk(cur, neg, &pk[8 * c], sum);
+                if (c < 3) tmem_wait_ld();
+            }
+        };
+        using yes = std::true_type;
+        using no = std::false_type;
+        // masked and unmasked tiles get separate straight-line copies (no per-chunk branches: the scheduler can overlap
+        // the tail of one chunk with the head of the next)
+        auto walk = [&](auto do_exp, auto do_max, const bool need_mask, const int lim, const float neg, uint32_t (&pk)[32],
+                        float2& sum, float& mx) {
+            if (need_mask) walk_m(do_exp, do_max, yes{}, lim, neg, pk, sum, mx);
+            else walk_m(do_exp, do_max, no{}, lim, neg, pk, sum, mx);
         };
 
         for (int n = blockIdx.x; n < ts.total; n += gridDim.x) {
@@ -310,39 +349,54 @@ flash_fwd_kernel_sm100_p4(const __grid_constant__ CUtensorMap tmQ, const __grid_
                 tc_fence_after();
                 if (r_in_tile == 0 && hh == 0) FA_TRACE_EVENT(t, its + j, 0);
                 uint32_t pk[32];
-                float sum;
-                float mx;
-                {
-                    float s[64];
-                    load_scores(s, need_mask, lim);
-                    if (r_in_tile == 0 && hh == 0) FA_TRACE_EVENT(t, its + j, 1);
-                    // max of the own half first (ALU pipe), published to the thread that owns the other half of this row
-                    float mxa = fmaxf(s[0], s[1]), mxb = fmaxf(s[2], s[3]), mxc = fmaxf(s[4], s[5]), mxd = fmaxf(s[6], s[7]);
-#pragma unroll
-                    for (int c = 8; c < 64; c += 8) {
-                        mxa = fmaxf(mxa, fmaxf(s[c], s[c + 1]));
-                        mxb = fmaxf(mxb, fmaxf(s[c + 2], s[c + 3]));
-                        mxc = fmaxf(mxc, fmaxf(s[c + 4], s[c + 5]));
-                        mxd = fmaxf(mxd, fmaxf(s[c + 6], s[c + 7]));
-                    }
-                    mx = fmaxf(fmaxf(mxa, mxb), fmaxf(mxc, mxd));
+                float2 sum = make_float2(0.f, 0.f);
+                float mx = -INFINITY;
+                if (j == 0) {       // no reference yet: exact row max (both halves) before the exponentials
+                    walk(no{}, yes{}, need_mask, lim, 0.f, pk, sum, mx);
                     sts32f(x_own, mx);
-                    if (j == 0) {       // no reference yet: exact row max before the exponentials
-                        named_bar_sync(pair_bar, 64);
-                        float mp;
-                        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(mp) : "r"(x_peer));
-                        m_ref = fmaxf(mx, mp);
-                    }
-                    const float neg = (m_ref == -INFINITY) ? 0.f : -m_ref * c2;
-                    sum = exp_half(s, neg, pk);   // speculative for j > 0: old reference, the vote below confirms it
-                }
-                if (r_in_tile == 0 && hh == 0) FA_TRACE_EVENT(t, its + j, 2);
-                if (j > 0) {
                     named_bar_sync(pair_bar, 64);
                     float mp;
-                    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(mp) : "r"(x_peer));
+                    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(mp) : "r"(x_own ^ (kBlockM * 4)));
+                    m_ref = fmaxf(mx, mp);
+                    const float neg = (m_ref == -INFINITY) ? 0.f : -m_ref * c2;
+                    walk(yes{}, no{}, need_mask, lim, neg, pk, sum, mx);
+                    if (r_in_tile == 0 && hh == 0) FA_TRACE_EVENT(t, its + j, 2);
+                } else {
+                    // speculative: exponentials with the old reference; the vote below confirms the reference (or sends
+                    // the warp pair through the rescale path)
+                    float neg = (m_ref == -INFINITY) ? 0.f : -m_ref * c2;
+#if FA_P4_SUMVOTE
+                    // No per-element max: every P is non-negative, so "tile sum <= 2^9" proves that no exponent exceeded 9
+                    // (the lazy-rescale bound); only a row whose sum is larger (or inf / NaN) pays for a true max.
+                    walk(yes{}, no{}, need_mask, lim, neg, pk, sum, mx);
+                    if (r_in_tile == 0 && hh == 0) FA_TRACE_EVENT(t, its + j, 2);
+                    const float hs = sum.x + sum.y;
+                    sts32f(x_own, hs);
+                    named_bar_sync(pair_bar, 64);
+                    float hp;
+                    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(hp) : "r"(x_own ^ (kBlockM * 4)));
+                    bool need = !(hs + hp <= 512.f) || (m_ref == -INFINITY);   // (a row without a reference yet must look at its max)
+                    if (__any_sync(0xffffffffu, need)) {
+                        float mxo = -INFINITY;
+                        walk(no{}, yes{}, need_mask, lim, neg, pk, sum, mxo);
+                        named_bar_sync(pair_bar, 64);          // both threads of the row have read the sums: slots reusable
+                        sts32f(x_own, mxo);
+                        named_bar_sync(pair_bar, 64);
+                        float mp2;
+                        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(mp2) : "r"(x_own ^ (kBlockM * 4)));
+                        mx = fmaxf(mxo, mp2);
+                        need = need && (mx > m_ref);
+                    }
+#else
+                    walk(yes{}, yes{}, need_mask, lim, neg, pk, sum, mx);
+                    if (r_in_tile == 0 && hh == 0) FA_TRACE_EVENT(t, its + j, 2);
+                    sts32f(x_own, mx);
+                    named_bar_sync(pair_bar, 64);
+                    float mp;
+                    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(mp) : "r"(x_own ^ (kBlockM * 4)));
                     mx = fmaxf(mx, mp);
                     const bool need = (mx - m_ref) * c2 > kRescaleThreshold;   // reference moves by more than 2^8
+#endif
                     if (__any_sync(0xffffffffu, need)) {
                         // slow path (both warps of the pair take it together: they see the same 32 row maxima):
                         // rescale the own half of O_t and the running sum, redo the exponentials with the new reference
@@ -362,12 +416,9 @@ flash_fwd_kernel_sm100_p4(const __grid_constant__ CUtensorMap tmQ, const __grid_
                             tmem_st32(tO + c * 32, o);
                         }
                         tmem_wait_st();
-                        {
-                            float s[64];
-                            load_scores(s, need_mask, lim);   // own S columns are still intact: own P not stored yet
-                            const float neg = (m_ref == -INFINITY) ? 0.f : -m_ref * c2;
-                            sum = exp_half(s, neg, pk);
-                        }
+                        neg = (m_ref == -INFINITY) ? 0.f : -m_ref * c2;
+                        sum = make_float2(0.f, 0.f);
+                        walk(yes{}, no{}, need_mask, lim, neg, pk, sum, mx);   // own S columns are intact: own P not stored yet
                         // P_t V of this step accumulates into ALL of O_t: neither half may release its P before both
                         // halves of the row block have finished rescaling
                         tc_fence_before();
@@ -380,7 +431,7 @@ flash_fwd_kernel_sm100_p4(const __grid_constant__ CUtensorMap tmQ, const __grid_
                 tmem_wait_st();
                 tc_fence_before();
                 mbar_arrive(&bar_p_full[2 * t + hh]);
-                l_run += sum;
+                l_run += sum.x + sum.y;
                 if (r_in_tile == 0 && hh == 0) FA_TRACE_EVENT(t, its + j, 4);
             }
             its += n_t;
@@ -392,7 +443,7 @@ flash_fwd_kernel_sm100_p4(const __grid_constant__ CUtensorMap tmQ, const __grid_
             sts32f(x_own, l_run);
             named_bar_sync(pair_bar, 64);
             float l_peer;
-            asm volatile("ld.shared.f32 %0, [%1];" : "=f"(l_peer) : "r"(x_peer));
+            asm volatile("ld.shared.f32 %0, [%1];" : "=f"(l_peer) : "r"(x_own ^ (kBlockM * 4)));
             const float l_tot = l_run + l_peer;
             const bool row_empty = (m_ref == -INFINITY) || !(l_tot > 0.f);   // no visible key: O = 0, LSE = 0
             const float inv_l = row_empty ? 0.f : (1.f / l_tot);
@@ -506,8 +557,8 @@ int launch_fwd_p4(const fa_fwd_params* p, const CUtensorMap& tq, const CUtensorM
 #define FA_INST(B, E)                                                                                                  \
     template int launch_fwd_p4<B, E>(const fa_fwd_params*, const CUtensorMap&, const CUtensorMap&, const CUtensorMap&,  \
                                      FwdParams, cudaStream_t);
-FA_INST(true, 0) FA_INST(true, 1) FA_INST(true, 2)
-FA_INST(false, 0) FA_INST(false, 1) FA_INST(false, 2)
+FA_INST(true, 0) FA_INST(true, 1) FA_INST(true, 2) FA_INST(true, 3) FA_INST(true, 4)
+FA_INST(false, 0) FA_INST(false, 1) FA_INST(false, 2) FA_INST(false, 3) FA_INST(false, 4)
 #undef FA_INST
 
 }  // namespace fa100

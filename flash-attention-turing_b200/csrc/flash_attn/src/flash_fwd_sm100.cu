@@ -639,26 +639,31 @@ static int launch_fwd_ws(const fa_fwd_params* p, const CUtensorMap& tq, const CU
     return FA_OK;
 }
 
-static int fwd_emu() {
-    // FA_B200_EMU=n: n of every 4 exponentials per row are evaluated by polynomial on the FMA pipe (tuning knob)
+static int fwd_variant() {
+    // FA_B200_FWD selects a kernel for A/B runs and debugging:
+    //   (unset) / "p4" = 3: persistent kernel with four softmax warpgroups for head_dim 128 (flash_fwd_p4_sm100.cu),
+    //                       the two-warpgroup persistent kernel for head_dim 64
+    //   "ws"           = 0: two-warpgroup persistent kernel for every head_dim (flash_fwd_persist_sm100.cu)
+    //   "np"           = 2: one CTA per work item (non-persistent) warp-specialised kernel
+    //   "g"            = 1: single-tile bring-up kernel
     static int v = -1;
     if (v < 0) {
-        const char* e = getenv("FA_B200_EMU");
-        // measured on B200: 1 of 4 pairs is +1.4 % in a 20-launch burst but -0.5 % once the 1 kW power cap governs
-        // (300-launch loop), 2 of 4 is slower in both; default off
-        v = e ? atoi(e) : 0;
-        if (v < 0 || v > 2) v = 0;
+        const char* e = getenv("FA_B200_FWD");
+        v = (e && e[0] == 'g') ? 1 : (e && e[0] == 'n') ? 2 : (e && e[0] == 'w') ? 0 : 3;
     }
     return v;
 }
 
-static int fwd_variant() {
-    // FA_B200_FWD selects a kernel for A/B runs and debugging: "g" = single-tile bring-up kernel, "np" = one CTA per
-    // work item (non-persistent) warp-specialised kernel; default = the persistent warp-specialised kernel
+static int fwd_emu() {
+    // FA_B200_EMU: share of the exponentials evaluated by a degree-3 polynomial on the FMA pipe instead of MUFU.EX2
+    //   0 = none, 4 = 1 pair in 8 (p4 only), 1 = 2 in 8, 3 = 3 in 8 (p4 only), 2 = 4 in 8.
+    // Default: 1 for the four-warpgroup kernel (measured +3 % over 0 and better than 4 / 3 / 2 at C2, C3 and C4, burst and
+    // sustained), 0 for the two-warpgroup kernels (there 1 is +1.4 % in a burst and -0.5 % under the power cap).
     static int v = -1;
     if (v < 0) {
-        const char* e = getenv("FA_B200_FWD");
-        v = (e && e[0] == 'g') ? 1 : (e && e[0] == 'n') ? 2 : (e && e[0] == 'p' && e[1] == '4') ? 3 : 0;
+        const char* e = getenv("FA_B200_EMU");
+        v = e ? atoi(e) : (fwd_variant() == 3 ? 1 : 0);
+        if (v < 0 || v > 4) v = 0;
     }
     return v;
 }
@@ -739,6 +744,8 @@ int launch_fwd_sm100(const fa_fwd_params* p, cudaStream_t stream) {
         switch (fwd_emu()) {
             case 0: return bf16 ? launch_fwd_p4<true, 0>(p, tq, tk, tv, kp, stream) : launch_fwd_p4<false, 0>(p, tq, tk, tv, kp, stream);
             case 1: return bf16 ? launch_fwd_p4<true, 1>(p, tq, tk, tv, kp, stream) : launch_fwd_p4<false, 1>(p, tq, tk, tv, kp, stream);
+            case 3: return bf16 ? launch_fwd_p4<true, 3>(p, tq, tk, tv, kp, stream) : launch_fwd_p4<false, 3>(p, tq, tk, tv, kp, stream);
+            case 4: return bf16 ? launch_fwd_p4<true, 4>(p, tq, tk, tv, kp, stream) : launch_fwd_p4<false, 4>(p, tq, tk, tv, kp, stream);
             default: return bf16 ? launch_fwd_p4<true, 2>(p, tq, tk, tv, kp, stream) : launch_fwd_p4<false, 2>(p, tq, tk, tv, kp, stream);
         }
     }
