@@ -62,7 +62,8 @@ template <int D> struct DqSmem {
 };
 namespace dqt { constexpr uint32_t kS = 0, kDP = 128, kDQ = 256, kDS = 384; }
 
-template <int D, bool kBf16>
+// kEmu (FA_B200_BWD_EMU=1, off by default): 2 of every 8 column pairs evaluate P = 2^x by polynomial on the FMA pipe
+template <int D, bool kBf16, bool kEmu>
 __global__ void __launch_bounds__(384, 1)
 flash_bwd_dq_kernel_sm100(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmDO,
                           const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
@@ -263,7 +264,7 @@ flash_bwd_dq_kernel_sm100(const __grid_constant__ CUtensorMap tmQ, const __grid_
 #pragma unroll
             for (int i = 0; i < 32; ++i) {
                 const float2 x = __ffma2_rn(make_float2(s[2 * i], s[2 * i + 1]), c2v, negv);
-                const float2 pr = make_float2(fast_exp2(x.x), fast_exp2(x.y));
+                const float2 pr = (kEmu && (i & 3) == 0) ? exp2_poly_pair(x) : make_float2(fast_exp2(x.x), fast_exp2(x.y));
                 const float2 ds = __fmul2_rn(pr, __fadd2_rn(make_float2(dp[2 * i], dp[2 * i + 1]), ndv));
                 pk[i] = pack2<kBf16>(ds.x, ds.y);
             }
@@ -336,7 +337,7 @@ template <int D> struct DkvSmem {
     static constexpr int kOffBar = kOffStat + 2 * 2 * kSubQ * 4;
     static constexpr int kBytes = kOffBar + 256 + 1024;
 };
-namespace kvt { constexpr uint32_t kSt = 0, kDPt = 64, kPt = 128, kDSt = 160, kDV = 256, kDK = 384; }
+namespace kvt { constexpr uint32_t kSt = 0, kDPt = 64, kPt = 128, kDSt = 160, kSt1 = 192, kDV = 256, kDK = 384; }   // S^T double-buffered: step st uses kSt (even) / kSt1 (odd)
 
 template <int D, bool kBf16>
 __global__ void __launch_bounds__(384, 1)
@@ -448,31 +449,47 @@ flash_bwd_dk_dv_kernel_sm100(const __grid_constant__ CUtensorMap tmQ, const __gr
             const uint32_t qk_lo = __shfl_sync(0xffffffffu, desc_lo(smem_u32(sQdO), 16), 0);             // K-major view
             const uint32_t qmn_lo = __shfl_sync(0xffffffffu, desc_lo(smem_u32(sQdO), L::kSubSlab), 0);   // MN-major view
             constexpr uint32_t kStage16 = (2 * L::kSub) >> 4, kSub16 = L::kSub >> 4;
-            auto issue_sdp = [&](int st) {
+            // S^T has two TMEM buffers, dP^T one.  S^T of step st+2 is issued right behind the accumulator MMAs of step st
+            // (its buffer was released by bar_s_empty(st)), so the tensor pipe never waits for the elementwise warpgroups
+            // to pick up step st+1 before it has more work: per step  dP^T(st+1) | dV,dK(st) | S^T(st+2).
+            auto issue_s = [&](int st) {
                 const int stage = st % L::kStages;
                 mbar_wait(&bar_qdo_full[stage], (st / L::kStages) & 1);
                 tc_fence_after();
                 if (leader) {
-                    const uint32_t qa = qk_lo + stage * kStage16, da = qa + kSub16;
-                    // S^T = K Q^T and dP^T = V dO^T, interleaved: two independent accumulation chains in flight
+                    const uint32_t qa = qk_lo + stage * kStage16;
+                    const uint32_t ts = tm + ((st & 1) ? kvt::kSt1 : kvt::kSt);
 #pragma unroll
                     for (int kk = 0; kk < D / 16; ++kk) {
                         const uint32_t oa = ((kk >> 2) * L::kSlab + (kk & 3) * 32) >> 4;
                         const uint32_t ob = ((kk >> 2) * L::kSubSlab + (kk & 3) * 32) >> 4;
-                        umma_ss(tm + kvt::kSt, desc_make(k_lo + oa, kDescHiK), desc_make(qa + ob, kDescHiK), idesc_st, kk > 0);
+                        umma_ss(ts, desc_make(k_lo + oa, kDescHiK), desc_make(qa + ob, kDescHiK), idesc_st, kk > 0);
+                    }
+                }
+            };
+            auto issue_dp = [&](int st) {   // the Q/dO stage of step st is already known to have landed (issue_s(st) waited)
+                const int stage = st % L::kStages;
+                if (leader) {
+                    const uint32_t da = qk_lo + stage * kStage16 + kSub16;
+#pragma unroll
+                    for (int kk = 0; kk < D / 16; ++kk) {
+                        const uint32_t oa = ((kk >> 2) * L::kSlab + (kk & 3) * 32) >> 4;
+                        const uint32_t ob = ((kk >> 2) * L::kSubSlab + (kk & 3) * 32) >> 4;
                         umma_ss(tm + kvt::kDPt, desc_make(v_lo + oa, kDescHiK), desc_make(da + ob, kDescHiK), idesc_st, kk > 0);
                     }
-                    tc_commit(bar_s_full);
+                    tc_commit(bar_s_full);      // S^T(st) was issued earlier on the same pipe: it has retired too
                 }
             };
             mbar_wait(bar_kv, 0);
-            issue_sdp(0);
+            issue_s(0);
+            issue_dp(0);
+            if (tot > 1) issue_s(1);
             for (int st = 0; st < tot; ++st) {
                 if (st + 1 < tot) {
-                    mbar_wait(bar_s_empty, st & 1);
+                    mbar_wait(bar_s_empty, st & 1);    // S^T(st), dP^T(st) are in registers: dP^T and S^T buffer (st & 1) are free
                     tc_fence_after();
                     if (lane == 0) FA_BTRACE(1, st, 0);
-                    issue_sdp(st + 1);
+                    issue_dp(st + 1);
                     if (lane == 0) FA_BTRACE(1, st, 1);
                 }
                 mbar_wait(bar_p_full, st & 1);
@@ -491,6 +508,7 @@ flash_bwd_dk_dv_kernel_sm100(const __grid_constant__ CUtensorMap tmQ, const __gr
                     tc_commit(&bar_qdo_empty[st % L::kStages]);
                     if (st + 1 == tot) tc_commit(bar_acc_full);
                 }
+                if (st + 2 < tot) issue_s(st + 2);
                 if (lane == 0) FA_BTRACE(1, st, 3);
                 __syncwarp();
             }
@@ -527,7 +545,8 @@ flash_bwd_dk_dv_kernel_sm100(const __grid_constant__ CUtensorMap tmQ, const __gr
         const int r = ((warp & 3) << 5) | lane;
         const int jg = n0 + r;                       // global key row of this thread
         const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
-        const uint32_t tSt = tmem_base + lane_base + kvt::kSt + g * 32;
+        const uint32_t tSt0 = tmem_base + lane_base + kvt::kSt + g * 32;
+        const uint32_t tSt1 = tmem_base + lane_base + kvt::kSt1 + g * 32;
         const uint32_t tDPt = tmem_base + lane_base + kvt::kDPt + g * 32;
         const uint32_t tPt = tmem_base + lane_base + kvt::kPt + g * 16;
         const uint32_t tDSt = tmem_base + lane_base + kvt::kDSt + g * 16;
@@ -541,7 +560,7 @@ flash_bwd_dk_dv_kernel_sm100(const __grid_constant__ CUtensorMap tmQ, const __gr
             tc_fence_after();
             if (tid == 0) FA_BTRACE(0, st, 0);
             float s[32], dp[32];
-            tmem_ld32(tSt, *reinterpret_cast<uint32_t(*)[32]>(&s[0]));
+            tmem_ld32((st & 1) ? tSt1 : tSt0, *reinterpret_cast<uint32_t(*)[32]>(&s[0]));
             tmem_ld32(tDPt, *reinterpret_cast<uint32_t(*)[32]>(&dp[0]));
             tmem_wait_ld();
             tc_fence_before();
@@ -646,10 +665,16 @@ template <int D, bool kBf16>
 static int launch_tc(const BwdParams& kp, const CUtensorMap& tq128, const CUtensorMap& tdo128, const CUtensorMap& tq64,
                      const CUtensorMap& tdo64, const CUtensorMap& tk, const CUtensorMap& tv, cudaStream_t stream) {
     static bool attr_set = false;
-    auto kdq = flash_bwd_dq_kernel_sm100<D, kBf16>;
+    // FA_B200_BWD_EMU=1: polynomial exponentials for 2 of 8 column pairs in the dQ kernel.  Measured: the elementwise phase
+    // drops from 1300 to 960 cycles per step, but the kernel is then bound by its MMA issue loop (1770 cycles per step
+    // either way; 2.89 vs 2.85 ms for the whole backward at C2) -> off by default, MUFU.EX2 everywhere.
+    static int dq_emu = -1;
+    if (dq_emu < 0) { const char* e = getenv("FA_B200_BWD_EMU"); dq_emu = e ? (atoi(e) != 0) : 0; }
+    auto kdq = dq_emu ? flash_bwd_dq_kernel_sm100<D, kBf16, true> : flash_bwd_dq_kernel_sm100<D, kBf16, false>;
     auto kkv = flash_bwd_dk_dv_kernel_sm100<D, kBf16>;
     if (!attr_set) {
-        FA_CUDA_CHECK(cudaFuncSetAttribute(kdq, cudaFuncAttributeMaxDynamicSharedMemorySize, DqSmem<D>::kBytes));
+        FA_CUDA_CHECK(cudaFuncSetAttribute(flash_bwd_dq_kernel_sm100<D, kBf16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, DqSmem<D>::kBytes));
+        FA_CUDA_CHECK(cudaFuncSetAttribute(flash_bwd_dq_kernel_sm100<D, kBf16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, DqSmem<D>::kBytes));
         FA_CUDA_CHECK(cudaFuncSetAttribute(kkv, cudaFuncAttributeMaxDynamicSharedMemorySize, DkvSmem<D>::kBytes));
         attr_set = true;
     }

@@ -278,6 +278,22 @@ FA_DEVICE float fast_exp2(float x) {
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
+// 2^x for a pair of floats on the FMA pipe (no MUFU): Cody-Waite split x = n + f, f in [-0.5, 0.5], degree-3 minimax
+// polynomial for 2^f (|rel err| < 7.5e-5, far below 16-bit rounding), exponent inserted with an integer add.
+// x is clamped to >= -125 (NaN / -inf -> 2^-125, i.e. zero after any 16-bit rounding); x must stay below 128.
+FA_DEVICE float2 exp2_poly_pair(float2 x) {
+    const float2 magic = make_float2(12582912.f, 12582912.f);                 // 1.5 * 2^23: low mantissa bits of x + magic = rint(x)
+    x = make_float2(fmaxf(x.x, -125.f), fmaxf(x.y, -125.f));
+    const float2 tt = __fadd2_rn(x, magic);
+    const float2 nnf = __ffma2_rn(tt, make_float2(-1.f, -1.f), magic);        // -rint(x), exact
+    const float2 f = __fadd2_rn(x, nnf);
+    float2 pl = __ffma2_rn(make_float2(0.05517115816473961f, 0.05517115816473961f), f,
+                           make_float2(0.2426101416349411f, 0.2426101416349411f));
+    pl = __ffma2_rn(pl, f, make_float2(0.6932609677314758f, 0.6932609677314758f));
+    pl = __ffma2_rn(pl, f, make_float2(0.9999281167984009f, 0.9999281167984009f));
+    return make_float2(__uint_as_float(__float_as_uint(pl.x) + (__float_as_uint(tt.x) << 23)),
+                       __uint_as_float(__float_as_uint(pl.y) + (__float_as_uint(tt.y) << 23)));
+}
 // pack two fp32 into one 32-bit word of two 16-bit floats: lo -> bits [0,16), hi -> bits [16,32)
 template <bool kBf16> FA_DEVICE uint32_t pack2(float lo, float hi) {
     uint32_t r;
