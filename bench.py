@@ -265,7 +265,8 @@ def main():
         ms_b = float(tb.item()) / n_b
         bwd = {"ms_per_step": ms_b, "value": 2.5 * flops_rank * world / (ms_b * 1e-3) / 1e12, "unit": "TFLOP/s (algorithmic 2.5x fwd)",
                "steps": n_b, "gpu_launches_per_step": bwd_launches,
-               "kernels": "flash_bwd_dot_do_o_kernel_sm100 + flash_bwd_dq_kernel_sm100 + flash_bwd_dk_dv_kernel_sm100"}
+               "kernels": "flash_bwd_dot_do_o_kernel_sm100 + flash_bwd_dk_dv_kernel_sm100_fused (dQ through fp32 bulk reductions) + "
+                          "flash_bwd_dq_kernel_sm100_convert; FA_B200_BWD=det selects the two deterministic kernels"}
         del do, g
 
     # ---- end to end through the public API with host buffers ----

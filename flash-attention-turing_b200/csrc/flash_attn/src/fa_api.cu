@@ -7,6 +7,7 @@
 #include <string.h>
 
 #include "fa_common.h"
+#include "flash_bwd_params.h"
 
 namespace fa100 {
 
@@ -124,8 +125,8 @@ int fa_b200_fwd(const fa_fwd_params* p, void* stream) {
 }
 
 int64_t fa_b200_bwd_workspace_bytes(const fa_fwd_params* p) {
-    (void)p;
-    return 0;
+    if (!p) return 0;
+    return bwd_fused_workspace_bytes(p->b, p->seqlen_q, p->h, p->d);   // 0 unless FA_B200_BWD=fused (fp32 dQ accumulator)
 }
 
 int fa_b200_bwd(const fa_bwd_params* p, void* stream) {

@@ -16,6 +16,8 @@ struct BwdParams {
     int is_causal;
     float scale;
     long long total_q, total_k;   // varlen: rows of the packed q / k tensors
+    float* dqacc;                 // fused backward only: fp32 dQ accumulator [b][h][sq_pad][d] (the C ABI's workspace)
+    int sq_pad;                   // sq rounded up to a multiple of 64
     long long* trace;             // FA_TRACE builds only
 };
 
@@ -32,5 +34,11 @@ struct BwdParams {
 // tensor-core (tcgen05) backward: dQ kernel + dK/dV kernel.  Returns FA_OK, or a negative value if this shape is
 // not handled (never happens for d in {64,128}).
 int launch_bwd_tc_sm100(const BwdParams& kp, bool bf16, cudaStream_t stream);
+
+// Fused backward (default; FA_B200_BWD=det switches it off): one K/V-stationary kernel produces dK, dV and — through fp32
+// bulk reductions into the workspace — dQ.  head_dim 128 only; needs a workspace of bwd_fused_workspace_bytes(); a caller
+// that passes no workspace gets the deterministic two-kernel path.
+bool bwd_fused_enabled();
+long long bwd_fused_workspace_bytes(long long b, long long sq_max, long long h, long long d);
 
 }  // namespace fa100

@@ -186,6 +186,7 @@ flash_bwd_dk_dv_kernel_sm100_rows(const BwdParams p) {
 
 static bool use_row_kernels() {
     // FA_B200_BWD=rows selects the CUDA-core any-shape kernels (debug / cross-check); default is the tcgen05 path
+    // (fused dQ/dK/dV kernel for head_dim 128, "det" = the two deterministic tcgen05 kernels)
     static int v = -1;
     if (v < 0) {
         const char* e = getenv("FA_B200_BWD");
@@ -231,6 +232,8 @@ int launch_bwd_sm100(const fa_bwd_params* p, cudaStream_t stream) {
     kp.hratio = (int)(f->h / f->h_k); kp.d = (int)f->d; kp.is_causal = f->is_causal;
     kp.scale = 1.0f / sqrtf((float)f->d);
     kp.total_q = f->total_q; kp.total_k = f->total_k; kp.trace = nullptr;
+    kp.dqacc = static_cast<float*>(p->workspace);
+    kp.sq_pad = (kp.sq + 63) / 64 * 64;
     const bool bf16 = f->dtype == FA_DTYPE_BF16;
     if (f->d == 128) return bf16 ? launch_bwd_rows<128, true>(kp, bf16, stream) : launch_bwd_rows<128, false>(kp, bf16, stream);
     if (f->d == 64) return bf16 ? launch_bwd_rows<64, true>(kp, bf16, stream) : launch_bwd_rows<64, false>(kp, bf16, stream);

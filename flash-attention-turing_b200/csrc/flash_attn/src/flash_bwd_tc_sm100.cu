@@ -658,6 +658,431 @@ flash_bwd_dk_dv_kernel_sm100(const __grid_constant__ CUtensorMap tmQ, const __gr
     }
 }
 
+
+// =================================================================================================
+// fused backward (default for head_dim 128 when the caller provides the workspace; FA_B200_BWD=det selects the two
+// deterministic kernels above): the dK/dV kernel also produces dQ, 5 GEMMs per tile pair instead of 7
+// =================================================================================================
+// Same K/V-stationary, transposed formulation as flash_bwd_dk_dv_kernel_sm100 (with a single S^T buffer), plus
+//     dQ^T[d x 64 q] = K^T dS^T      (A = the resident K tile read MN-major, B = dS^T from shared memory, MN-major)
+// per step, drained by the elementwise warpgroups into an fp32 accumulator [rows, h, d] in global memory with
+// red.global.add.f32 (coalesced: one q row x 32 consecutive d per warp instruction); flash_bwd_dq_kernel_sm100_convert
+// scales and rounds it to dQ afterwards.  Unlike everything else in this library the result depends on the order in
+// which the K/V tiles' contributions land (fp32 reductions in L2): dQ is not bit-reproducible run to run (dK and dV
+// are).  Measured +11 % (C2) to +17 % (C3, C4) over the two-kernel path; the kernel is bound by the L2's fp32 reduction
+// rate (~2 KB/clk for the whole chip, however the reductions are issued: scalar red 2.2, 512-byte bulk 1.3, 16 KB bulk 2.1).
+template <int D> struct FzSmem {
+    static constexpr int kSlab = kBM * 128;
+    static constexpr int kTile = kBM * D * 2;
+    static constexpr int kSubSlab = kSubQ * 128;
+    static constexpr int kSub = kSubQ * D * 2;
+    static constexpr int kStages = 3;                               // one less than the plain kernel: pays for the dQ staging tile
+    static constexpr int kOffK = 0;
+    static constexpr int kOffV = kTile;
+    static constexpr int kOffQdO = 2 * kTile;
+    static constexpr int kOffStat = kOffQdO + kStages * 2 * kSub;   // float [2 buffers][2][64]
+    static constexpr int kOffDS = kOffStat + 1024;                  // 2 x 16 KB, 1024-byte aligned
+    static constexpr int kOffDQ = kOffDS + 2 * kBM * kSubQ * 2;     // fp32 [64 q rows][128 d]: source of the bulk reductions
+    static constexpr int kOffBar = kOffDQ + kSubQ * D * 4;
+    static constexpr int kBytes = kOffBar + 256 + 1024;
+};
+static_assert(FzSmem<128>::kBytes <= 232448, "fused backward: shared memory budget");
+namespace fzt { constexpr uint32_t kSt = 0, kDPt = 64, kPt = 128, kDSt = 160, kDQt = 192, kDV = 256, kDK = 384; }
+
+template <int D, bool kBf16>
+__global__ void __launch_bounds__(384, 1)
+flash_bwd_dk_dv_kernel_sm100_fused(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmDO,
+                             const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
+                             const BwdParams p) {
+    using L = FzSmem<D>;
+    constexpr int kSlabs = D / 64;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, wg = warp >> 2;
+    const int n0 = blockIdx.x * kBM;
+    const int bidh_k = blockIdx.y, bidb = blockIdx.z;
+    const SeqGeom sg = seq_geom(p, bidb);
+    if (n0 >= sg.sk_b) return;
+    const int off = sg.sk_b - sg.sq_b;
+    // query rows that can see any key of this tile: i >= n0 - off (causal), in 64-row sub-tiles
+    const int i_first = p.is_causal ? max(0, n0 - off) : 0;
+    const int it0 = i_first / kSubQ;
+    const int nsub = (sg.sq_b + kSubQ - 1) / kSubQ;
+    const int steps_per_head = max(0, nsub - it0);
+    const int total = steps_per_head * p.hratio;
+    // The CTAs of one head (different K/V tiles) would all reduce into the SAME dQ rows at the same time if they walked
+    // the query sub-tiles in the same order — same-address reductions serialise in L2.  Each CTA therefore starts its walk
+    // at a different sub-tile (the order is irrelevant: the contributions commute).
+    const int rot = steps_per_head > 0 ? (int)((blockIdx.x * 2) % steps_per_head) : 0;
+    auto q_sub = [&](int st) { int ls = st % steps_per_head + rot; if (ls >= steps_per_head) ls -= steps_per_head; return it0 + ls; };
+    const int64_t krow_base = (p.cu_q != nullptr) ? (int64_t)sg.k_row0 : (int64_t)bidb * p.sk;
+    uint16_t* dk_base = reinterpret_cast<uint16_t*>(p.dk);
+    uint16_t* dv_base = reinterpret_cast<uint16_t*>(p.dv);
+    constexpr int kChunksPerRow = D / 8;
+
+    if (total == 0) {  // no query row sees these keys: dK = dV = 0
+        for (int idx = tid; idx < kBM * kChunksPerRow; idx += blockDim.x) {
+            const int rr = idx / kChunksPerRow, ch = idx % kChunksPerRow;
+            if (n0 + rr < sg.sk_b) {
+                const int64_t o = ((krow_base + n0 + rr) * p.h_k + bidh_k) * D;
+                *(reinterpret_cast<uint4*>(dk_base + o) + ch) = make_uint4(0, 0, 0, 0);
+                *(reinterpret_cast<uint4*>(dv_base + o) + ch) = make_uint4(0, 0, 0, 0);
+            }
+        }
+        return;
+    }
+
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* sK = smem + L::kOffK;
+    uint8_t* sV = smem + L::kOffV;
+    uint8_t* sQdO = smem + L::kOffQdO;
+    float* sStat = reinterpret_cast<float*>(smem + L::kOffStat);
+    uint8_t* sDS = smem + L::kOffDS;      // dS^T (16 bit) [2 buffers][128 kv rows][64 q = 128 B], 128B-swizzled: B operand of dQ^T
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::kOffBar);
+    uint64_t* bar_kv = bars;              // K + V landed
+    uint64_t* bar_qdo_full = bars + 1;                   // [kStages]
+    uint64_t* bar_qdo_empty = bars + 1 + L::kStages;     // [kStages]
+    uint64_t* bar_s_full = bars + 1 + 2 * L::kStages;
+    uint64_t* bar_s_empty = bar_s_full + 1;     // 256
+    uint64_t* bar_p_full = bar_s_full + 2;      // 256
+    uint64_t* bar_p_empty = bar_s_full + 3;
+    uint64_t* bar_acc_full = bar_s_full + 4;
+    uint64_t* bar_stat_full = bar_s_full + 5;   // [2] 64 arrivals (warps 10-11 published the column statistics)
+    uint64_t* bar_stat_empty = bar_s_full + 7;  // [2] 256 arrivals (every elementwise thread has them in registers)
+    uint64_t* bar_dq_full = bar_s_full + 9;     // dQ^T of a step complete in TMEM
+    uint64_t* bar_dq_empty = bar_s_full + 10;   // 256 threads have it in registers
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_s_full + 11);
+
+    if (warp == 8) {
+        if (lane == 0) {
+            mbar_init(bar_kv, 1);
+            for (int i = 0; i < L::kStages; ++i) { mbar_init(&bar_qdo_full[i], 1); mbar_init(&bar_qdo_empty[i], 1); }
+            mbar_init(bar_s_full, 1); mbar_init(bar_s_empty, 256);
+            mbar_init(bar_p_full, 256); mbar_init(bar_p_empty, 1);
+            mbar_init(bar_acc_full, 1);
+            mbar_init(bar_dq_full, 1); mbar_init(bar_dq_empty, 256);
+            for (int i = 0; i < 2; ++i) { mbar_init(&bar_stat_full[i], kSubQ); mbar_init(&bar_stat_empty[i], 256); }
+            fence_barrier_init();
+        }
+        __syncwarp();
+        tmem_alloc<512>(tmem_slot);
+        tmem_relinquish();
+    } else if (warp == 9 && lane == 0) {
+        tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmDO); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (wg == 2) {
+        setmaxnreg_dec<72>();
+        if (warp == 9) {
+            if (lane == 0) {
+                mbar_arrive_expect_tx(bar_kv, 2 * L::kTile);
+                for (int s = 0; s < kSlabs; ++s) {
+                    tma_load_4d(sK + s * L::kSlab, &tmK, bar_kv, s * 64, bidh_k, sg.k_row0 + n0, sg.tma_b);
+                    tma_load_4d(sV + s * L::kSlab, &tmV, bar_kv, s * 64, bidh_k, sg.k_row0 + n0, sg.tma_b);
+                }
+                for (int st = 0; st < total; ++st) {
+                    const int stage = st % L::kStages;
+                    const int hq = bidh_k * p.hratio + st / steps_per_head;
+                    const int it = q_sub(st);
+                    mbar_wait(&bar_qdo_empty[stage], ((st / L::kStages) & 1) ^ 1);
+                    mbar_arrive_expect_tx(&bar_qdo_full[stage], 2 * L::kSub);
+                    uint8_t* dst = sQdO + stage * 2 * L::kSub;
+                    for (int s = 0; s < kSlabs; ++s) {
+                        tma_load_4d(dst + s * L::kSubSlab, &tmQ, &bar_qdo_full[stage], s * 64, hq, sg.q_row0 + it * kSubQ, sg.tma_b);
+                        tma_load_4d(dst + L::kSub + s * L::kSubSlab, &tmDO, &bar_qdo_full[stage], s * 64, hq,
+                                    sg.q_row0 + it * kSubQ, sg.tma_b);
+                    }
+                }
+            }
+        } else if (warp == 8) {
+            const int tot = __shfl_sync(0xffffffffu, total, 0);
+            const bool leader = elect_one();
+            constexpr uint32_t idesc_st = make_idesc(kBf16, kBM, kSubQ, false, false);   // M=128 kv, N=64 q
+            constexpr uint32_t idesc_acc = make_idesc(kBf16, kBM, D, false, true);       // N = D, B MN-major
+            const uint32_t tm = __shfl_sync(0xffffffffu, tmem_base, 0);
+            const uint32_t k_lo = __shfl_sync(0xffffffffu, desc_lo(smem_u32(sK), 16), 0);
+            const uint32_t v_lo = __shfl_sync(0xffffffffu, desc_lo(smem_u32(sV), 16), 0);
+            const uint32_t qk_lo = __shfl_sync(0xffffffffu, desc_lo(smem_u32(sQdO), 16), 0);             // K-major view
+            const uint32_t qmn_lo = __shfl_sync(0xffffffffu, desc_lo(smem_u32(sQdO), L::kSubSlab), 0);   // MN-major view
+            constexpr uint32_t kStage16 = (2 * L::kSub) >> 4, kSub16 = L::kSub >> 4;
+            constexpr uint32_t idesc_dq = make_idesc(kBf16, D, kSubQ, true, true);       // dQ^T: M = d, N = 64 q, A and B MN-major
+            const uint32_t kmn_lo = __shfl_sync(0xffffffffu, desc_lo(smem_u32(sK), L::kSlab), 0);    // K^T as an MN-major A operand
+            const uint32_t ds_lo = __shfl_sync(0xffffffffu, desc_lo(smem_u32(sDS), 16), 0);
+            auto issue_sdp = [&](int st) {
+                const int stage = st % L::kStages;
+                mbar_wait(&bar_qdo_full[stage], (st / L::kStages) & 1);
+                tc_fence_after();
+                if (leader) {
+                    const uint32_t qa = qk_lo + stage * kStage16, da = qa + kSub16;
+#pragma unroll
+                    for (int kk = 0; kk < D / 16; ++kk) {
+                        const uint32_t oa = ((kk >> 2) * L::kSlab + (kk & 3) * 32) >> 4;
+                        const uint32_t ob = ((kk >> 2) * L::kSubSlab + (kk & 3) * 32) >> 4;
+                        umma_ss(tm + fzt::kSt, desc_make(k_lo + oa, kDescHiK), desc_make(qa + ob, kDescHiK), idesc_st, kk > 0);
+                        umma_ss(tm + fzt::kDPt, desc_make(v_lo + oa, kDescHiK), desc_make(da + ob, kDescHiK), idesc_st, kk > 0);
+                    }
+                    tc_commit(bar_s_full);
+                }
+            };
+            mbar_wait(bar_kv, 0);
+            issue_sdp(0);
+            for (int st = 0; st < tot; ++st) {
+                if (st + 1 < tot) {
+                    mbar_wait(bar_s_empty, st & 1);
+                    tc_fence_after();
+                    if (lane == 0) FA_BTRACE(1, st, 0);
+                    issue_sdp(st + 1);
+                    if (lane == 0) FA_BTRACE(1, st, 1);
+                }
+                mbar_wait(bar_p_full, st & 1);
+                tc_fence_after();
+                if (lane == 0) FA_BTRACE(1, st, 2);
+                if (leader) {
+                    const uint32_t qa = qmn_lo + (st % L::kStages) * kStage16, da = qa + kSub16;
+#pragma unroll
+                    for (int kk = 0; kk < kSubQ / 16; ++kk) {  // dV += P^T dO and dK += dS^T Q, interleaved
+                        umma_ts(tm + fzt::kDV, tm + fzt::kPt + kk * 8, desc_make(da + kk * (2048 >> 4), kDescHiK), idesc_acc,
+                                (st > 0 || kk > 0));
+                        umma_ts(tm + fzt::kDK, tm + fzt::kDSt + kk * 8, desc_make(qa + kk * (2048 >> 4), kDescHiK), idesc_acc,
+                                (st > 0 || kk > 0));
+                    }
+                    tc_commit(bar_p_empty);                          // P^T / dS^T in TMEM are free once these retire
+                    tc_commit(&bar_qdo_empty[st % L::kStages]);
+                }
+                // dQ^T(st) [d x 64 q] = K^T dS^T(st): its TMEM tile must have been drained by the elementwise warps
+                if (st > 0) { mbar_wait(bar_dq_empty, (st - 1) & 1); tc_fence_after(); }
+                if (leader) {
+                    const uint32_t dsa = ds_lo + (st & 1) * (uint32_t)((kBM * kSubQ * 2) >> 4);
+#pragma unroll
+                    for (int kk = 0; kk < kBM / 16; ++kk)
+                        umma_ss(tm + fzt::kDQt, desc_make(kmn_lo + kk * (2048 >> 4), kDescHiK), desc_make(dsa + kk * (2048 >> 4), kDescHiK),
+                                idesc_dq, kk > 0);
+                    tc_commit(bar_dq_full);
+                    if (st + 1 == tot) tc_commit(bar_acc_full);
+                }
+                if (lane == 0) FA_BTRACE(1, st, 3);
+                __syncwarp();
+            }
+        } else {
+            // ===================== warps 10-11: column statistics loader =====================
+            // thread c of the 64 stages -LSE*log2e and -D of query row (sub-tile row c) for every step, two buffers ahead
+            const int c = tid - 320;
+            auto fetch = [&](int st, float& lse_raw, float& d_raw, bool& ok) {   // issue the two global loads, no use yet
+                const int hq = bidh_k * p.hratio + st / steps_per_head;
+                const int i = q_sub(st) * kSubQ + c;
+                ok = i < sg.sq_b;
+                const int64_t o = ((int64_t)bidb * p.h + hq) * p.sq + (ok ? i : 0);
+                lse_raw = p.lse[o];
+                d_raw = p.dsum[o];
+            };
+            float lse_cur, d_cur, lse_nxt = 0.f, d_nxt = 0.f;
+            bool ok_cur, ok_nxt = false;
+            fetch(0, lse_cur, d_cur, ok_cur);
+            for (int st = 0; st < total; ++st) {
+                const int buf = st & 1;
+                if (st + 1 < total) fetch(st + 1, lse_nxt, d_nxt, ok_nxt);   // one step ahead: latency hidden behind the wait
+                mbar_wait(&bar_stat_empty[buf], ((st >> 1) & 1) ^ 1);
+                float* dst = sStat + buf * 2 * kSubQ;
+                dst[c] = ok_cur ? (-lse_cur * kLog2e) : -INFINITY;      // -inf => P = 0 for query rows beyond the sequence
+                dst[kSubQ + c] = ok_cur ? -d_cur : 0.f;
+                mbar_arrive(&bar_stat_full[buf]);
+                lse_cur = lse_nxt; d_cur = d_nxt; ok_cur = ok_nxt;
+            }
+        }
+    } else {
+        // ===== elementwise warpgroups: thread (g, r) owns key row r and query columns [32 g, 32 g + 32) of the sub-tile =====
+        setmaxnreg_inc<216>();
+        const int g = wg;
+        const int r = ((warp & 3) << 5) | lane;
+        const int jg = n0 + r;                       // global key row of this thread
+        const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+        const uint32_t tSt = tmem_base + lane_base + fzt::kSt + g * 32;
+        const uint32_t tDQt = tmem_base + lane_base + fzt::kDQt + g * 32;
+        // dQ^T of step s sits in TMEM as [d = lane][64 q columns]; warpgroup g adds its 32 columns into the fp32 dQ
+        // accumulator in global memory: for a fixed q row the 32 lanes of a warp hit 128 contiguous bytes
+        // ... then each warpgroup transposes its 32 columns through shared memory ([32 q rows][128 d] fp32) and 32 of its
+        // threads issue one 512-byte bulk reduction (cp.reduce.async.bulk ... add.f32) per q row.  (Per-thread
+        // red.global.add.f32 was tried first: 8192 scalar reductions per step stall the elementwise warps for ~2200
+        // cycles, the whole backward got 10 % slower.)
+        const uint32_t sDQg = smem_u32(smem + L::kOffDQ) + g * (32 * D * 4);
+        const int tw = tid & 127;                    // thread index inside the warpgroup
+        auto drain_dq = [&](int s) {
+            mbar_wait(bar_dq_full, s & 1);
+            tc_fence_after();
+            uint32_t v[32];
+            tmem_ld32(tDQt, v);
+            tmem_wait_ld();
+            tc_fence_before();
+            mbar_arrive(bar_dq_empty);
+            if (tid == 0) FA_BTRACE(0, s + 1, 6);
+            if (tw == 0) tma_store_wait_read<0>();   // the previous step's bulk reduction has read the staging rows
+            named_bar_sync(2 + g, 128);
+            if (tid == 0) FA_BTRACE(0, s + 1, 7);
+#pragma unroll
+            for (int c = 0; c < 32; ++c)             // row c of the staging tile, element d = r: 32 lanes -> 128 contiguous bytes
+                asm volatile("st.shared.b32 [%0], %1;" ::"r"(sDQg + c * (D * 4) + r * 4), "r"(v[c]) : "memory");
+            fence_proxy_async_smem();
+            named_bar_sync(2 + g, 128);
+            if (tw == 0) {
+                // the accumulator is head-major ([b][h][sq_pad][d], sq_pad a multiple of 64), so the 32 q rows of this
+                // warpgroup are ONE contiguous 16 KB block: a single bulk reduction per warpgroup and step.  (512-byte
+                // per-row reductions into a [rows][h][d] accumulator ran at a third of this rate: request-bound.)
+                const int hq = bidh_k * p.hratio + s / steps_per_head;
+                const int i0 = q_sub(s) * kSubQ + g * 32;
+                float* dst = p.dqacc + (((int64_t)bidb * p.h + hq) * p.sq_pad + i0) * D;
+                asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;"
+                             ::"l"(dst), "r"(sDQg), "n"(32 * D * 4) : "memory");
+                tma_store_commit();
+            }
+        };
+        const uint32_t tDPt = tmem_base + lane_base + fzt::kDPt + g * 32;
+        const uint32_t tPt = tmem_base + lane_base + fzt::kPt + g * 16;
+        const uint32_t tDSt = tmem_base + lane_base + fzt::kDSt + g * 16;
+        const float c2 = p.scale * kLog2e;
+        const float2 c2v = make_float2(c2, c2);
+
+        for (int st = 0; st < total; ++st) {
+            const int it = q_sub(st);
+            const int buf = st & 1;
+            mbar_wait(bar_s_full, st & 1);
+            tc_fence_after();
+            if (tid == 0) FA_BTRACE(0, st, 0);
+            float s[32], dp[32];
+            tmem_ld32(tSt, *reinterpret_cast<uint32_t(*)[32]>(&s[0]));
+            tmem_ld32(tDPt, *reinterpret_cast<uint32_t(*)[32]>(&dp[0]));
+            tmem_wait_ld();
+            tc_fence_before();
+            mbar_arrive(bar_s_empty);                // lets the MMA warp issue S^T/dP^T of the next step right away
+            // per-column statistics (-LSE*log2e, -D) of this sub-tile, staged by warps 10-11 (broadcast LDS.128).
+            // They are read AFTER the arrive on purpose: all the arithmetic below depends on them, which keeps the
+            // scheduler from sinking the TMEM loads / the arrive underneath the exponentials (measured: that delayed the
+            // next step's MMAs by ~700 cycles).
+            if (tid == 0) FA_BTRACE(0, st, 4);
+            mbar_wait(&bar_stat_full[buf], (st >> 1) & 1);
+            if (tid == 0) FA_BTRACE(0, st, 5);
+            const uint32_t stat = smem_u32(sStat) + (buf * 2 * kSubQ + g * 32) * 4;
+            float4 nl4[8], dd4[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                nl4[i] = lds128(stat + i * 16);
+                dd4[i] = lds128(stat + kSubQ * 4 + i * 16);
+            }
+
+            // causal: key jg visible to query i iff jg <= i + off  <=>  column c >= jg - off - it*64 - 32 g
+            const bool need_mask = p.is_causal && (it * kSubQ < n0 + kBM - 1 - off);
+            const int cmin = need_mask ? (jg - off - it * kSubQ - g * 32) : 0;
+            uint32_t pkp[16], pkd[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                const float2 nl = (i & 1) ? make_float2(nl4[i >> 1].z, nl4[i >> 1].w) : make_float2(nl4[i >> 1].x, nl4[i >> 1].y);
+                const float2 dd = (i & 1) ? make_float2(dd4[i >> 1].z, dd4[i >> 1].w) : make_float2(dd4[i >> 1].x, dd4[i >> 1].y);
+                const float2 x = __ffma2_rn(make_float2(s[2 * i], s[2 * i + 1]), c2v, nl);
+                float2 pr = make_float2(fast_exp2(x.x), fast_exp2(x.y));
+                if (need_mask) {
+                    if (2 * i < cmin) pr.x = 0.f;
+                    if (2 * i + 1 < cmin) pr.y = 0.f;
+                }
+                const float2 ds = __fmul2_rn(pr, __fadd2_rn(make_float2(dp[2 * i], dp[2 * i + 1]), dd));
+                pkp[i] = pack2<kBf16>(pr.x, pr.y);
+                pkd[i] = pack2<kBf16>(ds.x, ds.y);
+            }
+            if (jg >= sg.sk_b) {     // key rows beyond the sequence (varlen: the next sequence's rows) must not reach dQ
+#pragma unroll
+                for (int i = 0; i < 16; ++i) { pkp[i] = 0u; pkd[i] = 0u; }
+            }
+            if (tid == 0) FA_BTRACE(0, st, 1);
+            mbar_arrive(&bar_stat_empty[buf]);       // statistics consumed
+            if (st > 0) mbar_wait(bar_p_empty, (st - 1) & 1);
+            if (tid == 0) FA_BTRACE(0, st, 2);
+            tmem_st16(tPt, pkp);
+            tmem_st16(tDSt, pkd);
+            {   // dS^T also goes to shared memory (buffer st & 1) as the MN-major B operand of dQ^T: row r, 16-byte chunks 4g..4g+3
+                const uint32_t row_addr = smem_u32(sDS) + (st & 1) * (kBM * kSubQ * 2) + r * 128;
+#pragma unroll
+                for (int c = 0; c < 4; ++c)
+                    sts128u(row_addr + (((g * 4 + c) ^ (r & 7)) << 4), make_uint4(pkd[4 * c], pkd[4 * c + 1], pkd[4 * c + 2], pkd[4 * c + 3]));
+            }
+            fence_proxy_async_smem();
+            tmem_wait_st();
+            tc_fence_before();
+            mbar_arrive(bar_p_full);
+            if (tid == 0) FA_BTRACE(0, st, 3);
+            if (st > 0) drain_dq(st - 1);
+        }
+        drain_dq(total - 1);
+        if (tw == 0) tma_store_wait<0>();            // all bulk reductions of this thread have completed
+
+        // ---- epilogue: dV, dK * scale -> 16 bit -> smem (dead V / K tiles) -> coalesced stores ----
+        mbar_wait(bar_acc_full, 0);
+        tc_fence_after();
+        constexpr int kHalfD = D / 2;
+#pragma unroll
+        for (int which = 0; which < 2; ++which) {
+            const uint32_t tA = tmem_base + lane_base + (which == 0 ? fzt::kDV : fzt::kDK) + g * kHalfD;
+            uint8_t* sO = which == 0 ? sV : sK;
+            const float mul = which == 0 ? 1.f : p.scale;
+#pragma unroll
+            for (int c = 0; c < kHalfD / 32; ++c) {
+                uint32_t o[32];
+                tmem_ld32(tA + c * 32, o);
+                tmem_wait_ld();
+#pragma unroll
+                for (int q4 = 0; q4 < 4; ++q4) {
+                    uint4 v;
+                    v.x = pack2<kBf16>(__uint_as_float(o[q4 * 8 + 0]) * mul, __uint_as_float(o[q4 * 8 + 1]) * mul);
+                    v.y = pack2<kBf16>(__uint_as_float(o[q4 * 8 + 2]) * mul, __uint_as_float(o[q4 * 8 + 3]) * mul);
+                    v.z = pack2<kBf16>(__uint_as_float(o[q4 * 8 + 4]) * mul, __uint_as_float(o[q4 * 8 + 5]) * mul);
+                    v.w = pack2<kBf16>(__uint_as_float(o[q4 * 8 + 6]) * mul, __uint_as_float(o[q4 * 8 + 7]) * mul);
+                    const int chunk = g * (kHalfD / 8) + c * 4 + q4;
+                    *reinterpret_cast<uint4*>(sO + r * (D * 2) + ((chunk ^ (r & 7)) * 16)) = v;
+                }
+            }
+        }
+        tc_fence_before();
+        named_bar_sync(1, 256);
+#pragma unroll 2
+        for (int idx = tid; idx < kBM * kChunksPerRow; idx += 256) {
+            const int rr = idx / kChunksPerRow, ch = idx % kChunksPerRow;
+            if (n0 + rr < sg.sk_b) {
+                const int64_t o = ((krow_base + n0 + rr) * p.h_k + bidh_k) * D;
+                const int so = rr * (D * 2) + ((ch ^ (rr & 7)) * 16);
+                *(reinterpret_cast<uint4*>(dv_base + o) + ch) = *reinterpret_cast<const uint4*>(sV + so);
+                *(reinterpret_cast<uint4*>(dk_base + o) + ch) = *reinterpret_cast<const uint4*>(sK + so);
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 8) {
+        tc_fence_after();
+        tmem_dealloc<512>(tmem_base);
+    }
+}
+
+
+// dQ[b, i, h, :] = round16(scale * acc[b, h, i, :]): 16 lanes x 8 elements per row, 16 rows per block, HBM-bound
+template <bool kBf16>
+__global__ void __launch_bounds__(256)
+flash_bwd_dq_kernel_sm100_convert(const BwdParams p) {
+    constexpr int D = 128;
+    const int bidb = blockIdx.z, bidh = blockIdx.y;
+    const int i = blockIdx.x * 16 + (threadIdx.x >> 4), ch = threadIdx.x & 15;
+    int q_row0 = 0, sq_b = p.sq;
+    if (p.cu_q) { q_row0 = p.cu_q[bidb]; sq_b = p.cu_q[bidb + 1] - q_row0; }
+    if (i >= sq_b) return;
+    const int64_t row_base = p.cu_q ? (int64_t)q_row0 : (int64_t)bidb * p.sq;
+    const float4* src = reinterpret_cast<const float4*>(p.dqacc + (((int64_t)bidb * p.h + bidh) * p.sq_pad + i) * D) + 2 * ch;
+    const float4 a = src[0], b = src[1];
+    uint4 o;
+    o.x = pack2<kBf16>(a.x * p.scale, a.y * p.scale); o.y = pack2<kBf16>(a.z * p.scale, a.w * p.scale);
+    o.z = pack2<kBf16>(b.x * p.scale, b.y * p.scale); o.w = pack2<kBf16>(b.z * p.scale, b.w * p.scale);
+    reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.dq) + ((row_base + i) * p.h + bidh) * D)[ch] = o;
+}
+
 // =================================================================================================
 // host
 // =================================================================================================
@@ -735,6 +1160,59 @@ static int launch_tc(const BwdParams& kp, const CUtensorMap& tq128, const CUtens
     return FA_OK;
 }
 
+bool bwd_fused_enabled() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("FA_B200_BWD"); v = (!e || e[0] == 'f') ? 1 : 0; }   // default; "det" / "rows" select the others
+    return v == 1;
+}
+long long bwd_fused_workspace_bytes(long long b, long long sq_max, long long h, long long d) {
+    // fp32 accumulator [b][h][sq_pad][d], sq_pad = sq_max rounded up to the 64-row step of the kernel
+    return (bwd_fused_enabled() && d == 128) ? b * h * ((sq_max + 63) / 64 * 64) * d * 4 : 0;
+}
+
+template <bool kBf16>
+static int launch_fused(const BwdParams& kp, const CUtensorMap& tq64, const CUtensorMap& tdo64, const CUtensorMap& tk,
+                        const CUtensorMap& tv, cudaStream_t stream) {
+    constexpr int D = 128;
+    static bool attr_set = false;
+    auto kern = flash_bwd_dk_dv_kernel_sm100_fused<D, kBf16>;
+    if (!attr_set) {
+        FA_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, FzSmem<D>::kBytes));
+        attr_set = true;
+    }
+    FA_CUDA_CHECK(cudaMemsetAsync(kp.dqacc, 0, (size_t)bwd_fused_workspace_bytes(kp.b, kp.sq, kp.h, D), stream));
+    dim3 g((kp.sk + kBM - 1) / kBM, kp.h_k, kp.b);
+#ifdef FA_TRACE
+    if (getenv("FA_B200_TRACE")) {
+        BwdParams kt = kp;
+        static long long* d_trace = nullptr;
+        if (!d_trace) cudaMalloc(&d_trace, 2 * 64 * 8 * sizeof(long long));
+        cudaMemsetAsync(d_trace, 0, 2 * 64 * 8 * sizeof(long long), stream);
+        kt.trace = d_trace;
+        kern<<<g, 384, FzSmem<D>::kBytes, stream>>>(tq64, tdo64, tk, tv, kt);
+        cudaStreamSynchronize(stream);
+        static long long hh[2 * 64 * 8];
+        cudaMemcpy(hh, d_trace, sizeof(hh), cudaMemcpyDeviceToHost);
+        const long long t0 = hh[0];
+        for (int r = 0; r < 2; ++r)
+            for (int j = 0; j < 10; ++j) {
+                printf("BTRACE fused %d %2d :", r, j);
+                for (int e = 0; e < 8; ++e) printf(" %8lld", hh[(r * 64 + j) * 8 + e] ? hh[(r * 64 + j) * 8 + e] - t0 : -1LL);
+                printf("\n");
+            }
+        fflush(stdout);
+    } else
+#endif
+    kern<<<g, 384, FzSmem<D>::kBytes, stream>>>(tq64, tdo64, tk, tv, kp);
+    FA_CUDA_CHECK(cudaGetLastError());
+    count_launch();
+    dim3 gc((kp.sq + 15) / 16, kp.h, kp.b);
+    flash_bwd_dq_kernel_sm100_convert<kBf16><<<gc, 256, 0, stream>>>(kp);
+    FA_CUDA_CHECK(cudaGetLastError());
+    count_launch();
+    return FA_OK;
+}
+
 int launch_bwd_tc_sm100(const BwdParams& kp, bool bf16, cudaStream_t stream) {
     const bool varlen = kp.cu_q != nullptr;
     const uint64_t D = (uint64_t)kp.d;
@@ -760,6 +1238,8 @@ int launch_bwd_tc_sm100(const BwdParams& kp, bool bf16, cudaStream_t stream) {
         if ((rc = encode_tmap_4d(&tk, kp.k, bf16, dims, str, box128)) != FA_OK) return rc;
         if ((rc = encode_tmap_4d(&tv, kp.v, bf16, dims, str, box128)) != FA_OK) return rc;
     }
+    if (kp.d == 128 && bwd_fused_enabled() && kp.dqacc != nullptr)
+        return bf16 ? launch_fused<true>(kp, tq64, tdo64, tk, tv, stream) : launch_fused<false>(kp, tq64, tdo64, tk, tv, stream);
     if (kp.d == 128) return bf16 ? launch_tc<128, true>(kp, tq128, tdo128, tq64, tdo64, tk, tv, stream)
                                  : launch_tc<128, false>(kp, tq128, tdo128, tq64, tdo64, tk, tv, stream);
     if (kp.d == 64) return bf16 ? launch_tc<64, true>(kp, tq128, tdo128, tq64, tdo64, tk, tv, stream)

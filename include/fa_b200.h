@@ -70,7 +70,9 @@ typedef struct fa_bwd_params {
     void* dk;                   /* dk_ptr  [.., h_k, d]  (GQA group-sum is done inside; the reference */
     void* dv;                   /* dv_ptr   needs h-expanded buffers + torch::sum_out, flash_api.cpp:265-312) */
     float* dsum;                /* do_o_ptr: scratch fp32 [b, h, seqlen_q] = rowsum(dO * O) */
-    void* workspace;            /* device scratch of fa_b200_bwd_workspace_bytes() bytes (may be NULL if 0) */
+    void* workspace;            /* device scratch of fa_b200_bwd_workspace_bytes() bytes: the fp32 dQ accumulator of the
+                                   fused backward (head_dim 128).  NULL is always allowed: the library then runs the two
+                                   deterministic kernels (dQ, dK/dV) that mirror the reference's structure */
 } fa_bwd_params;
 
 /* replaces run_mha_fwd (flash_api.cpp:139-145).  Asynchronous on `stream` (a cudaStream_t). */
@@ -79,7 +81,7 @@ int fa_b200_fwd(const fa_fwd_params* p, void* stream);
 /* replaces run_mha_bwd (flash_api.cpp:147-153): dsum preprocess + dQ + dK/dV on `stream`. */
 int fa_b200_bwd(const fa_bwd_params* p, void* stream);
 
-/* bytes of device scratch fa_b200_bwd needs for these sizes (0 if none) */
+/* bytes of device scratch fa_b200_bwd can use for these sizes (0 if none) */
 int64_t fa_b200_bwd_workspace_bytes(const fa_fwd_params* p);
 
 /* number of kernel launches the last fa_b200_fwd / fa_b200_bwd call on this thread enqueued */

@@ -94,7 +94,7 @@ def fwd(q, k, v, causal, cu_q=None, cu_k=None, max_sq=None, max_sk=None):
     return o, lse
 
 
-def bwd(q, k, v, o, lse, dout, causal, cu_q=None, cu_k=None, max_sq=None, max_sk=None):
+def bwd(q, k, v, o, lse, dout, causal, cu_q=None, cu_k=None, max_sq=None, max_sk=None, use_workspace=True):
     import torch
     lib = load()
     dq, dk, dv = torch.zeros_like(q), torch.zeros_like(k), torch.zeros_like(v)
@@ -102,7 +102,7 @@ def bwd(q, k, v, o, lse, dout, causal, cu_q=None, cu_k=None, max_sq=None, max_sk
     p = BwdParams()
     p.fwd = make_fwd_params(q, k, v, o, lse, causal, cu_q, cu_k, max_sq, max_sk)
     p.dout, p.dq, p.dk, p.dv, p.dsum = dout.data_ptr(), dq.data_ptr(), dk.data_ptr(), dv.data_ptr(), dsum.data_ptr()
-    nbytes = lib.fa_b200_bwd_workspace_bytes(ctypes.byref(p.fwd))
+    nbytes = lib.fa_b200_bwd_workspace_bytes(ctypes.byref(p.fwd)) if use_workspace else 0
     ws = torch.empty(max(int(nbytes), 1), device=q.device, dtype=torch.uint8)
     p.workspace = ws.data_ptr() if nbytes > 0 else None
     rc = lib.fa_b200_bwd(ctypes.byref(p), ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
