@@ -193,6 +193,19 @@ def main():
 
     torch.cuda.set_device(local_rank)
     if world > 1:
+        # pin this rank to the CPUs next to its GPU so that its pinned host buffers (the e2e leg) are first-touched on the
+        # local NUMA node; best effort (no NVML / no permission -> unchanged)
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            hnd = pynvml.nvmlDeviceGetHandleByIndex(local_rank)
+            words = pynvml.nvmlDeviceGetCpuAffinity(hnd, (os.cpu_count() + 63) // 64)
+            near = {64 * w + bit for w, word in enumerate(words) for bit in range(64) if (word >> bit) & 1}
+            allowed = near & set(os.sched_getaffinity(0))
+            if allowed:
+                os.sched_setaffinity(0, allowed)
+        except Exception:
+            pass
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     dev = torch.device("cuda", local_rank)
     dt = torch.bfloat16
