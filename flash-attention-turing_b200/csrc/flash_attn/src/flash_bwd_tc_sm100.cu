@@ -18,12 +18,17 @@
 // Unlike the forward, nothing is aliased in TMEM (S, dP, dS/P and the accumulators have their own columns), so the
 // MMAs of step j+1 are issued as soon as step j's S/dP have been read into registers and run underneath the
 // elementwise work of step j.
+#include <cuda_fp16.h>
 #include <math.h>
 #include <stdlib.h>
 
 #include "fa_common.h"
 #include "flash_bwd_params.h"
 #include "sm100_ptx.cuh"
+
+#ifndef FA_FUSED_RED_COLS
+#define FA_FUSED_RED_COLS 16   // query rows per step whose dQ leaves through red.global (the rest: one bulk reduction)
+#endif
 
 namespace fa100 {
 
@@ -689,8 +694,10 @@ template <int D> struct FzSmem {
 static_assert(FzSmem<128>::kBytes <= 232448, "fused backward: shared memory budget");
 namespace fzt { constexpr uint32_t kSt = 0, kDPt = 64, kPt = 128, kDSt = 160, kDQt = 192, kDV = 256, kDK = 384; }
 
-template <int D, bool kBf16>
-__global__ void __launch_bounds__(384, 1)
+// kAcc16 (FA_B200_BWD_ACC=16, experiment): the partial dQ tiles are reduced in fp16 instead of fp32 (half the L2 reduction
+// bytes; the running sums are rounded to 11 bits at every one of the sk/128 additions)
+template <int D, bool kBf16, bool kAcc16>
+__global__ void __launch_bounds__(512, 1)
 flash_bwd_dk_dv_kernel_sm100_fused(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmDO,
                              const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
                              const BwdParams p) {
@@ -759,7 +766,7 @@ flash_bwd_dk_dv_kernel_sm100_fused(const __grid_constant__ CUtensorMap tmQ, cons
             mbar_init(bar_s_full, 1); mbar_init(bar_s_empty, 256);
             mbar_init(bar_p_full, 256); mbar_init(bar_p_empty, 1);
             mbar_init(bar_acc_full, 1);
-            mbar_init(bar_dq_full, 1); mbar_init(bar_dq_empty, 256);
+            mbar_init(bar_dq_full, 1); mbar_init(bar_dq_empty, 128);
             for (int i = 0; i < 2; ++i) { mbar_init(&bar_stat_full[i], kSubQ); mbar_init(&bar_stat_empty[i], 256); }
             fence_barrier_init();
         }
@@ -774,7 +781,75 @@ flash_bwd_dk_dv_kernel_sm100_fused(const __grid_constant__ CUtensorMap tmQ, cons
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    if (wg == 2) {
+    if (wg == 3) {
+        // ===================== warpgroup 3: dQ^T drain (TMEM -> shared staging tile -> one bulk reduction per step) =====================
+        // dQ^T of step s sits in TMEM as [d = lane][64 q columns]; thread r = d writes row c, element r of the staging tile
+        // (32 lanes -> 128 contiguous bytes), then ONE thread issues a single cp.reduce.async.bulk of the whole tile: the
+        // accumulator is head-major ([b][h][sq_pad][d]) so the 64 q rows of a step are contiguous in global memory.
+        // (Tried first, see DESIGN.md: per-thread red.global.add.f32, per-row 512-byte bulk reductions, and draining from
+        //  the elementwise warpgroups — all slower.)
+        setmaxnreg_dec<40>();
+        const int tw = tid & 127;
+        const int r = ((warp & 3) << 5) | lane;
+        const uint32_t tDQt = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + fzt::kDQt;
+        const uint32_t sDQr = smem_u32(smem + L::kOffDQ) + r * (kAcc16 ? 2 : 4);
+        // The bulk-reduction engine of an SM moves ~15 B/clk: 32 KB of fp32 per step would take longer than the step's MMAs.
+        // The first kRedCols query rows of every step therefore leave through per-thread red.global.add.f32 straight from
+        // registers (a different path: LSU -> L2), the rest through the staging tile and ONE bulk reduction.
+        constexpr int kRedCols = kAcc16 ? 0 : FA_FUSED_RED_COLS;
+        constexpr int kBulkRows = kSubQ - kRedCols;
+        for (int s = 0; s < total; ++s) {
+            const int hq = bidh_k * p.hratio + s / steps_per_head;
+            const int64_t eoff = (((int64_t)bidb * p.h + hq) * p.sq_pad + (int64_t)q_sub(s) * kSubQ) * D;
+            mbar_wait(bar_dq_full, s & 1);
+            tc_fence_after();
+#pragma unroll
+            for (int qt = 0; qt < 4; ++qt) {                 // 16 columns at a time: this warpgroup lives on 40 registers
+                uint32_t v[16];
+                tmem_ld16(tDQt + qt * 16, v);
+                tmem_wait_ld();
+                if (qt == 3) {
+                    tc_fence_before();
+                    mbar_arrive(bar_dq_empty);               // dQ^T(s) is in registers: the next step's MMA may overwrite it
+                }
+                if (qt * 16 < kRedCols) {
+                    float* dst = p.dqacc + eoff + (qt * 16) * D + r;
+#pragma unroll
+                    for (int c = 0; c < 16; ++c)
+                        asm volatile("red.global.add.f32 [%0], %1;" ::"l"(dst + c * D), "f"(__uint_as_float(v[c])) : "memory");
+                } else {
+                    if (qt * 16 == kRedCols) {
+                        if (tw == 0) tma_store_wait_read<0>();   // the previous step's bulk reduction has read the staging tile
+                        named_bar_sync(2, 128);
+                    }
+#pragma unroll
+                    for (int c = 0; c < 16; ++c) {
+                        if constexpr (kAcc16) {
+                            uint16_t hv;
+                            asm("cvt.rn.f16.f32 %0, %1;" : "=h"(hv) : "f"(__uint_as_float(v[c])));
+                            asm volatile("st.shared.b16 [%0], %1;" ::"r"(sDQr + (qt * 16 - kRedCols + c) * (D * 2)), "h"(hv) : "memory");
+                        } else {
+                            asm volatile("st.shared.b32 [%0], %1;" ::"r"(sDQr + (qt * 16 - kRedCols + c) * (D * 4)), "r"(v[c]) : "memory");
+                        }
+                    }
+                }
+            }
+            fence_proxy_async_smem();
+            named_bar_sync(2, 128);
+            if (tw == 0) {
+                const uint32_t sDQ = smem_u32(smem + L::kOffDQ);
+                if constexpr (kAcc16) {
+                    asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.noftz.f16 [%0], [%1], %2;"
+                                 ::"l"(reinterpret_cast<uint16_t*>(p.dqacc) + eoff), "r"(sDQ), "n"(kSubQ * D * 2) : "memory");
+                } else {
+                    asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;"
+                                 ::"l"(p.dqacc + eoff + kRedCols * D), "r"(sDQ), "n"(kBulkRows * D * 4) : "memory");
+                }
+                tma_store_commit();
+            }
+        }
+        if (tw == 0) tma_store_wait<0>();            // all bulk reductions have completed before the CTA retires
+    } else if (wg == 2) {
         setmaxnreg_dec<72>();
         if (warp == 9) {
             if (lane == 0) {
@@ -894,50 +969,12 @@ flash_bwd_dk_dv_kernel_sm100_fused(const __grid_constant__ CUtensorMap tmQ, cons
         }
     } else {
         // ===== elementwise warpgroups: thread (g, r) owns key row r and query columns [32 g, 32 g + 32) of the sub-tile =====
-        setmaxnreg_inc<216>();
+        setmaxnreg_inc<200>();
         const int g = wg;
         const int r = ((warp & 3) << 5) | lane;
         const int jg = n0 + r;                       // global key row of this thread
         const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
         const uint32_t tSt = tmem_base + lane_base + fzt::kSt + g * 32;
-        const uint32_t tDQt = tmem_base + lane_base + fzt::kDQt + g * 32;
-        // dQ^T of step s sits in TMEM as [d = lane][64 q columns]; warpgroup g adds its 32 columns into the fp32 dQ
-        // accumulator in global memory: for a fixed q row the 32 lanes of a warp hit 128 contiguous bytes
-        // ... then each warpgroup transposes its 32 columns through shared memory ([32 q rows][128 d] fp32) and 32 of its
-        // threads issue one 512-byte bulk reduction (cp.reduce.async.bulk ... add.f32) per q row.  (Per-thread
-        // red.global.add.f32 was tried first: 8192 scalar reductions per step stall the elementwise warps for ~2200
-        // cycles, the whole backward got 10 % slower.)
-        const uint32_t sDQg = smem_u32(smem + L::kOffDQ) + g * (32 * D * 4);
-        const int tw = tid & 127;                    // thread index inside the warpgroup
-        auto drain_dq = [&](int s) {
-            mbar_wait(bar_dq_full, s & 1);
-            tc_fence_after();
-            uint32_t v[32];
-            tmem_ld32(tDQt, v);
-            tmem_wait_ld();
-            tc_fence_before();
-            mbar_arrive(bar_dq_empty);
-            if (tid == 0) FA_BTRACE(0, s + 1, 6);
-            if (tw == 0) tma_store_wait_read<0>();   // the previous step's bulk reduction has read the staging rows
-            named_bar_sync(2 + g, 128);
-            if (tid == 0) FA_BTRACE(0, s + 1, 7);
-#pragma unroll
-            for (int c = 0; c < 32; ++c)             // row c of the staging tile, element d = r: 32 lanes -> 128 contiguous bytes
-                asm volatile("st.shared.b32 [%0], %1;" ::"r"(sDQg + c * (D * 4) + r * 4), "r"(v[c]) : "memory");
-            fence_proxy_async_smem();
-            named_bar_sync(2 + g, 128);
-            if (tw == 0) {
-                // the accumulator is head-major ([b][h][sq_pad][d], sq_pad a multiple of 64), so the 32 q rows of this
-                // warpgroup are ONE contiguous 16 KB block: a single bulk reduction per warpgroup and step.  (512-byte
-                // per-row reductions into a [rows][h][d] accumulator ran at a third of this rate: request-bound.)
-                const int hq = bidh_k * p.hratio + s / steps_per_head;
-                const int i0 = q_sub(s) * kSubQ + g * 32;
-                float* dst = p.dqacc + (((int64_t)bidb * p.h + hq) * p.sq_pad + i0) * D;
-                asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;"
-                             ::"l"(dst), "r"(sDQg), "n"(32 * D * 4) : "memory");
-                tma_store_commit();
-            }
-        };
         const uint32_t tDPt = tmem_base + lane_base + fzt::kDPt + g * 32;
         const uint32_t tPt = tmem_base + lane_base + fzt::kPt + g * 16;
         const uint32_t tDSt = tmem_base + lane_base + fzt::kDSt + g * 16;
@@ -1010,10 +1047,7 @@ flash_bwd_dk_dv_kernel_sm100_fused(const __grid_constant__ CUtensorMap tmQ, cons
             tc_fence_before();
             mbar_arrive(bar_p_full);
             if (tid == 0) FA_BTRACE(0, st, 3);
-            if (st > 0) drain_dq(st - 1);
         }
-        drain_dq(total - 1);
-        if (tw == 0) tma_store_wait<0>();            // all bulk reductions of this thread have completed
 
         // ---- epilogue: dV, dK * scale -> 16 bit -> smem (dead V / K tiles) -> coalesced stores ----
         mbar_wait(bar_acc_full, 0);
@@ -1065,7 +1099,7 @@ flash_bwd_dk_dv_kernel_sm100_fused(const __grid_constant__ CUtensorMap tmQ, cons
 
 
 // dQ[b, i, h, :] = round16(scale * acc[b, h, i, :]): 16 lanes x 8 elements per row, 16 rows per block, HBM-bound
-template <bool kBf16>
+template <bool kBf16, bool kAcc16>
 __global__ void __launch_bounds__(256)
 flash_bwd_dq_kernel_sm100_convert(const BwdParams p) {
     constexpr int D = 128;
@@ -1075,8 +1109,17 @@ flash_bwd_dq_kernel_sm100_convert(const BwdParams p) {
     if (p.cu_q) { q_row0 = p.cu_q[bidb]; sq_b = p.cu_q[bidb + 1] - q_row0; }
     if (i >= sq_b) return;
     const int64_t row_base = p.cu_q ? (int64_t)q_row0 : (int64_t)bidb * p.sq;
-    const float4* src = reinterpret_cast<const float4*>(p.dqacc + (((int64_t)bidb * p.h + bidh) * p.sq_pad + i) * D) + 2 * ch;
-    const float4 a = src[0], b = src[1];
+    const int64_t eoff = (((int64_t)bidb * p.h + bidh) * p.sq_pad + i) * D + 8 * ch;
+    float4 a, b;
+    if constexpr (kAcc16) {
+        const uint4 w = *reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(p.dqacc) + eoff);
+        const float2 f0 = __half22float2(*reinterpret_cast<const __half2*>(&w.x)), f1 = __half22float2(*reinterpret_cast<const __half2*>(&w.y));
+        const float2 f2 = __half22float2(*reinterpret_cast<const __half2*>(&w.z)), f3 = __half22float2(*reinterpret_cast<const __half2*>(&w.w));
+        a = make_float4(f0.x, f0.y, f1.x, f1.y); b = make_float4(f2.x, f2.y, f3.x, f3.y);
+    } else {
+        const float4* src = reinterpret_cast<const float4*>(p.dqacc + eoff);
+        a = src[0]; b = src[1];
+    }
     uint4 o;
     o.x = pack2<kBf16>(a.x * p.scale, a.y * p.scale); o.y = pack2<kBf16>(a.z * p.scale, a.w * p.scale);
     o.z = pack2<kBf16>(b.x * p.scale, b.y * p.scale); o.w = pack2<kBf16>(b.z * p.scale, b.w * p.scale);
@@ -1170,17 +1213,23 @@ long long bwd_fused_workspace_bytes(long long b, long long sq_max, long long h, 
     return (bwd_fused_enabled() && d == 128) ? b * h * ((sq_max + 63) / 64 * 64) * d * 4 : 0;
 }
 
-template <bool kBf16>
+static bool bwd_acc16() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("FA_B200_BWD_ACC"); v = (e && atoi(e) == 16) ? 1 : 0; }
+    return v == 1;
+}
+
+template <bool kBf16, bool kAcc16>
 static int launch_fused(const BwdParams& kp, const CUtensorMap& tq64, const CUtensorMap& tdo64, const CUtensorMap& tk,
                         const CUtensorMap& tv, cudaStream_t stream) {
     constexpr int D = 128;
     static bool attr_set = false;
-    auto kern = flash_bwd_dk_dv_kernel_sm100_fused<D, kBf16>;
+    auto kern = flash_bwd_dk_dv_kernel_sm100_fused<D, kBf16, kAcc16>;
     if (!attr_set) {
         FA_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, FzSmem<D>::kBytes));
         attr_set = true;
     }
-    FA_CUDA_CHECK(cudaMemsetAsync(kp.dqacc, 0, (size_t)bwd_fused_workspace_bytes(kp.b, kp.sq, kp.h, D), stream));
+    FA_CUDA_CHECK(cudaMemsetAsync(kp.dqacc, 0, (size_t)bwd_fused_workspace_bytes(kp.b, kp.sq, kp.h, D) / (kAcc16 ? 2 : 1), stream));
     dim3 g((kp.sk + kBM - 1) / kBM, kp.h_k, kp.b);
 #ifdef FA_TRACE
     if (getenv("FA_B200_TRACE")) {
@@ -1189,7 +1238,7 @@ static int launch_fused(const BwdParams& kp, const CUtensorMap& tq64, const CUte
         if (!d_trace) cudaMalloc(&d_trace, 2 * 64 * 8 * sizeof(long long));
         cudaMemsetAsync(d_trace, 0, 2 * 64 * 8 * sizeof(long long), stream);
         kt.trace = d_trace;
-        kern<<<g, 384, FzSmem<D>::kBytes, stream>>>(tq64, tdo64, tk, tv, kt);
+        kern<<<g, 512, FzSmem<D>::kBytes, stream>>>(tq64, tdo64, tk, tv, kt);
         cudaStreamSynchronize(stream);
         static long long hh[2 * 64 * 8];
         cudaMemcpy(hh, d_trace, sizeof(hh), cudaMemcpyDeviceToHost);
@@ -1203,11 +1252,11 @@ static int launch_fused(const BwdParams& kp, const CUtensorMap& tq64, const CUte
         fflush(stdout);
     } else
 #endif
-    kern<<<g, 384, FzSmem<D>::kBytes, stream>>>(tq64, tdo64, tk, tv, kp);
+    kern<<<g, 512, FzSmem<D>::kBytes, stream>>>(tq64, tdo64, tk, tv, kp);
     FA_CUDA_CHECK(cudaGetLastError());
     count_launch();
     dim3 gc((kp.sq + 15) / 16, kp.h, kp.b);
-    flash_bwd_dq_kernel_sm100_convert<kBf16><<<gc, 256, 0, stream>>>(kp);
+    flash_bwd_dq_kernel_sm100_convert<kBf16, kAcc16><<<gc, 256, 0, stream>>>(kp);
     FA_CUDA_CHECK(cudaGetLastError());
     count_launch();
     return FA_OK;
@@ -1239,7 +1288,8 @@ int launch_bwd_tc_sm100(const BwdParams& kp, bool bf16, cudaStream_t stream) {
         if ((rc = encode_tmap_4d(&tv, kp.v, bf16, dims, str, box128)) != FA_OK) return rc;
     }
     if (kp.d == 128 && bwd_fused_enabled() && kp.dqacc != nullptr)
-        return bf16 ? launch_fused<true>(kp, tq64, tdo64, tk, tv, stream) : launch_fused<false>(kp, tq64, tdo64, tk, tv, stream);
+        return bwd_acc16() ? (bf16 ? launch_fused<true, true>(kp, tq64, tdo64, tk, tv, stream) : launch_fused<false, true>(kp, tq64, tdo64, tk, tv, stream))
+                           : (bf16 ? launch_fused<true, false>(kp, tq64, tdo64, tk, tv, stream) : launch_fused<false, false>(kp, tq64, tdo64, tk, tv, stream));
     if (kp.d == 128) return bf16 ? launch_tc<128, true>(kp, tq128, tdo128, tq64, tdo64, tk, tv, stream)
                                  : launch_tc<128, false>(kp, tq128, tdo128, tq64, tdo64, tk, tv, stream);
     if (kp.d == 64) return bf16 ? launch_tc<64, true>(kp, tq128, tdo128, tq64, tdo64, tk, tv, stream)
