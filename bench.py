@@ -66,6 +66,30 @@ def measured_peaks():
         return {"burst": 1590.0, "sustained": 1400.0, "hbm_gbs": 6650.0, "source": "B200_PROFILING.md fallback (of fallback)"}
 
 
+def bind_near_gpu(index):
+    """Restrict this process to the CPUs next to GPU `index` (NVML affinity mask) so that pinned host buffers are
+    first-touched on the GPU's NUMA node; returns the previous affinity (None if nothing was changed).  Best effort."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        try:   # CUDA_VISIBLE_DEVICES may reorder devices: look the GPU up by its PCI address
+            import torch
+            pr = torch.cuda.get_device_properties(index)
+            hnd = pynvml.nvmlDeviceGetHandleByPciBusId(f"{pr.pci_domain_id:08x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0".encode())
+        except Exception:
+            hnd = pynvml.nvmlDeviceGetHandleByIndex(index)
+        words = pynvml.nvmlDeviceGetCpuAffinity(hnd, (os.cpu_count() + 63) // 64)
+        near = {64 * w + bit for w, word in enumerate(words) for bit in range(64) if (word >> bit) & 1}
+        prev = os.sched_getaffinity(0)
+        allowed = near & set(prev)
+        if allowed and allowed != set(prev):
+            os.sched_setaffinity(0, allowed)
+            return prev
+    except Exception:
+        pass
+    return None
+
+
 class ClockSampler:
     """samples nvidia-smi clocks / throttle reasons while the timed region runs"""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -193,19 +217,6 @@ def main():
 
     torch.cuda.set_device(local_rank)
     if world > 1:
-        # pin this rank to the CPUs next to its GPU so that its pinned host buffers (the e2e leg) are first-touched on the
-        # local NUMA node; best effort (no NVML / no permission -> unchanged)
-        try:
-            import pynvml
-            pynvml.nvmlInit()
-            hnd = pynvml.nvmlDeviceGetHandleByIndex(local_rank)
-            words = pynvml.nvmlDeviceGetCpuAffinity(hnd, (os.cpu_count() + 63) // 64)
-            near = {64 * w + bit for w, word in enumerate(words) for bit in range(64) if (word >> bit) & 1}
-            allowed = near & set(os.sched_getaffinity(0))
-            if allowed:
-                os.sched_setaffinity(0, allowed)
-        except Exception:
-            pass
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     dev = torch.device("cuda", local_rank)
     dt = torch.bfloat16
@@ -285,6 +296,7 @@ def main():
     # ---- end to end through the public API with host buffers ----
     e2e = None
     if not args.no_e2e:
+        prev_aff = bind_near_gpu(local_rank)   # host buffers on the GPU's NUMA node (restored below for the CPU baseline)
         hq, hk, hv = (torch.randn(b, s, h, d, dtype=dt).pin_memory() for _ in range(3))
         ho = torch.empty(b, s, h, d, dtype=dt).pin_memory()
         hl = torch.empty(b, h, s, dtype=torch.float32).pin_memory()
@@ -310,7 +322,9 @@ def main():
                "h2d_bytes_per_step": 3 * q.numel() * 2, "d2h_bytes_per_step": o.numel() * 2 + lse.numel() * 4,
                "ms_per_step": ms_e2e, "steps": n_e2e, "api": "flash_attn_turing.fwd_host(q,k,v,is_causal) on pinned host buffers: per-batch chunks, H2D / kernel / "
                       "D2H overlapped on three streams; every step moves all inputs up and all outputs down",
-               "gpu_launches_per_step": b}
+               "gpu_launches_per_step": b, "numa_bound": prev_aff is not None}
+        if prev_aff is not None:
+            os.sched_setaffinity(0, prev_aff)
 
     if rank == 0:
         peaks = measured_peaks()
