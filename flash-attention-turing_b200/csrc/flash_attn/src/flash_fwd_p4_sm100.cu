@@ -21,6 +21,18 @@
 // 64-thread named barrier per warp pair; the exponentials still start speculatively with the old reference.
 #include <type_traits>
 
+// Two experiments on the item-to-item transition (clock64 trace: ~3600 cycles from a tile's last P to its first S of the
+// next item, against 1260 inside an item).  Both were measured neutral (+-1 % at S1k / C2 / C3 / C4,
+// profiles/r01s2_run19.log, r01s2_run20.log), so the simpler configuration stays the default:
+//   FA_P4_STAGING2  1: three K/V ring stages + one O staging tile PER query tile, TMA stores issued by helper warps 18/19
+//                   0: four ring stages + one shared staging tile behind a lock, store issued (and awaited) by a softmax thread
+//   FA_P4_QPREFETCH 1: the TMA producer fetches the next item's Q tiles from inside its waits for K/V ring slots
+#ifndef FA_P4_STAGING2
+#define FA_P4_STAGING2 0
+#endif
+#ifndef FA_P4_QPREFETCH
+#define FA_P4_QPREFETCH 0
+#endif
 #ifndef FA_P4_SUMVOTE
 #define FA_P4_SUMVOTE 1   // 0: per-element row max + vote (A/B builds); 1: vote on the tile sum, max only when it trips
 #endif
@@ -46,7 +58,7 @@ flash_fwd_kernel_sm100_p4(const __grid_constant__ CUtensorMap tmQ, const __grid_
                           const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmO,
                           const FwdParams p, const TileSched ts) {
     constexpr int kSlabs = D / 64;
-    constexpr int kStages = L::kKvStages;
+    constexpr int kStages = FA_P4_STAGING2 ? 3 : L::kKvStages;
 
     const int tid = threadIdx.x;
     const int warp = tid >> 5;
@@ -58,7 +70,8 @@ flash_fwd_kernel_sm100_p4(const __grid_constant__ CUtensorMap tmQ, const __grid_
     if (smem - smem_raw > kBytesP4 - kNeedP4) { asm volatile("trap;"); }   // cannot happen with a >= 256-byte aligned window
     uint8_t* sQ = smem + L::kOffQ;
     uint8_t* sKV = smem + L::kOffKV;
-    uint8_t* sStage = smem + L::kOffStage;
+    // with two staging tiles the K/V ring gives up one slot: same total (Q 64 KB + ring + staging = 224 KB)
+    uint8_t* sStage = smem + L::kOffKV + kStages * L::kTile;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kOffBars);
     uint64_t* bar_q_full = bars;                      // [2]  Q_t landed
     uint64_t* bar_q_empty = bars + 2;                 // [2]  last S_t MMA of the item retired
@@ -69,7 +82,8 @@ flash_fwd_kernel_sm100_p4(const __grid_constant__ CUtensorMap tmQ, const __grid_
     uint64_t* bar_o_full = bar_p_full + 4;            // [2]  last P V of the item retired
     uint64_t* bar_o_empty = bar_o_full + 2;           // [2]  epilogue has O_t in registers (256 arrivals)
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_o_empty + 2);
-    int* stage_lock = reinterpret_cast<int*>(tmem_slot + 1);   // the two tiles' epilogues share one staging tile
+    int* stage_lock = reinterpret_cast<int*>(tmem_slot + 1);   // FA_P4_STAGING2 == 0: the two tiles' epilogues share one staging tile
+    uint64_t* bar_stage_free = bars + 28;             // [2] FA_P4_STAGING2: the TMA store of tile t has read its staging tile
     const uint32_t xch = smem_u32(smem + kOffXch);
 
     if (warp == 16) {
@@ -82,6 +96,7 @@ flash_fwd_kernel_sm100_p4(const __grid_constant__ CUtensorMap tmQ, const __grid_
                 mbar_init(&bar_o_full[t], 1); mbar_init(&bar_o_empty[t], 2 * kBlockM);
             }
             for (int i = 0; i < kStages; ++i) { mbar_init(&bar_kv_full[i], 1); mbar_init(&bar_kv_empty[i], 1); }
+            mbar_init(&bar_stage_free[0], 1); mbar_init(&bar_stage_free[1], 1);
             fence_barrier_init();
         }
         __syncwarp();
@@ -102,14 +117,46 @@ flash_fwd_kernel_sm100_p4(const __grid_constant__ CUtensorMap tmQ, const __grid_
             if (lane == 0) {
                 int kv_i = 0;            // running K/V ring index
                 int nq[2] = {0, 0};      // Q_t loads so far
+                bool q_ahead[2] = {false, false};   // Q_t of the item being started was already issued during the previous item
                 for (int n = blockIdx.x; n < ts.total; n += gridDim.x) {
                     const WorkItem w = decode_item(ts, n, p.h, p.is_causal != 0);
                     const ItemGeom g = item_geom(p, w);
                     if (g.skip || g.n_blocks == 0) continue;
                     const int bidh_k = w.bidh / p.hratio;
+                    // The next item's Q tiles do not go through the K/V ring: as soon as the last S_t MMA of this item has
+                    // retired (bar_q_empty[t]) they are fetched, from inside the waits for ring slots below.  Without this the
+                    // Q loads were only issued once every K/V load of the current item was out, and the first S of the next
+                    // item arrived ~1500 cycles after the softmax warps were ready for it (clock64 trace).
+                    const int nn = n + gridDim.x;
+                    bool nvalid = FA_P4_QPREFETCH && nn < ts.total;
+                    WorkItem w2 = w;
+                    ItemGeom g2 = g;
+                    if (nvalid) {
+                        w2 = decode_item(ts, nn, p.h, p.is_causal != 0);
+                        g2 = item_geom(p, w2);
+                        nvalid = !(g2.skip || g2.n_blocks == 0);
+                    }
+                    bool q_next[2] = {false, false};
+                    bool own_q_done = false;
+                    auto issue_q = [&](const WorkItem& wi, const ItemGeom& gi, int t) {
+                        mbar_arrive_expect_tx(&bar_q_full[t], L::kTile);
+                        for (int s = 0; s < kSlabs; ++s)
+                            tma_load_4d(sQ + t * L::kTile + s * L::kSlab, &tmQ, &bar_q_full[t], s * 64, wi.bidh,
+                                        gi.q_row0 + gi.m0 + t * kBlockM, gi.tma_b);
+                        ++nq[t];
+                    };
+                    auto try_prefetch_q = [&]() {
+                        if (!nvalid || !own_q_done) return;
+#pragma unroll
+                        for (int t = 0; t < 2; ++t)
+                            if (!q_next[t] && g2.nblk[t] > 0 && mbar_try_wait(&bar_q_empty[t], (nq[t] & 1) ^ 1)) {
+                                issue_q(w2, g2, t);
+                                q_next[t] = true;
+                            }
+                    };
                     auto load_kv = [&](const CUtensorMap* tm, int j) {
                         const int slot = kv_i % kStages;
-                        mbar_wait(&bar_kv_empty[slot], ((kv_i / kStages) & 1) ^ 1);
+                        while (!mbar_try_wait(&bar_kv_empty[slot], ((kv_i / kStages) & 1) ^ 1)) try_prefetch_q();
                         mbar_arrive_expect_tx(&bar_kv_full[slot], L::kTile);
                         for (int s = 0; s < kSlabs; ++s)
                             tma_load_4d(sKV + slot * L::kTile + s * L::kSlab, tm, &bar_kv_full[slot], s * 64, bidh_k,
@@ -118,21 +165,21 @@ flash_fwd_kernel_sm100_p4(const __grid_constant__ CUtensorMap tmQ, const __grid_
                     };
                     auto load_q = [&](int t) {
                         if (g.nblk[t] == 0) return;
+                        if (q_ahead[t]) return;                  // issued while the previous item was still running
                         mbar_wait(&bar_q_empty[t], (nq[t] & 1) ^ 1);
-                        mbar_arrive_expect_tx(&bar_q_full[t], L::kTile);
-                        for (int s = 0; s < kSlabs; ++s)
-                            tma_load_4d(sQ + t * L::kTile + s * L::kSlab, &tmQ, &bar_q_full[t], s * 64, w.bidh,
-                                        g.q_row0 + g.m0 + t * kBlockM, g.tma_b);
-                        ++nq[t];
+                        issue_q(w, g, t);
                     };
                     load_q(0);
                     load_kv(&tmK, 0);
                     load_q(1);
+                    own_q_done = true;
                     load_kv(&tmV, 0);
                     for (int j = 1; j < g.n_blocks; ++j) {
                         load_kv(&tmK, j);
                         load_kv(&tmV, j);
                     }
+                    try_prefetch_q();
+                    q_ahead[0] = q_next[0]; q_ahead[1] = q_next[1];
                 }
             }
         } else if (warp == 16) {
@@ -222,6 +269,34 @@ flash_fwd_kernel_sm100_p4(const __grid_constant__ CUtensorMap tmQ, const __grid_
                 nitem[0] += (nb0 > 0); nitem[1] += (nb1 > 0);
             }
         }
+#if FA_P4_STAGING2
+        else {
+            // ===================== warps 18 / 19: TMA store of tile slot 0 / 1 =====================
+            // The softmax warpgroups only write the staging tile and arrive on a named barrier; waiting for the bulk
+            // engine to read 32 KB of shared memory (~1800 cycles, measured) is this warp's job, not theirs.
+            const int t = warp - 18;
+            for (int n = blockIdx.x; n < ts.total; n += gridDim.x) {
+                const WorkItem w = decode_item(ts, n, p.h, p.is_causal != 0);
+                const ItemGeom g = item_geom(p, w);
+                if (g.skip) continue;
+                const int mt = g.m0 + t * kBlockM;
+                if (mt >= g.sq_b || g.nblk[t] == 0) continue;
+                const bool whole_tile = (mt + kBlockM <= g.sq_b) || (p.cu_q == nullptr);
+                if (!whole_tile) continue;                         // ragged varlen tail: stored by the softmax threads themselves
+                named_bar_sync(11 + t, 2 * kBlockM + 32);          // staging tile t written and fenced by its 256 threads
+                if (lane == 0) {
+#pragma unroll
+                    for (int sl = 0; sl < kSlabs; ++sl)
+                        tma_store_4d(&tmO, sStage + t * L::kTile + sl * L::kSlab, sl * 64, w.bidh, g.q_row0 + mt, g.tma_b);
+                    tma_store_commit();
+                    tma_store_wait_read<0>();
+                    mbar_arrive(&bar_stage_free[t]);
+                }
+                __syncwarp();
+            }
+            if (lane == 0) tma_store_wait<0>();                    // all bulk stores have landed before the CTA retires
+        }
+#endif
     } else {
         // ========== softmax warpgroups: warpgroup 2t+hh owns columns [64hh, 64hh+64) of tile slot t, one thread per row ==========
         setmaxnreg_inc<104>();
@@ -240,6 +315,7 @@ flash_fwd_kernel_sm100_p4(const __grid_constant__ CUtensorMap tmQ, const __grid_
         const float inv_c2 = p.inv_scale_log2;
         int its = 0;       // S_t steps so far
         int nitem = 0;     // items with keys finished by this slot
+        int nstore = 0;    // FA_P4_STAGING2: TMA stores of this slot handed to the helper warp so far
 
         // The 64 scores of a thread are walked in four chunks of 16 columns (tcgen05.ld x16), the next chunk in flight
         // while the current one is processed: only 32 score registers are ever live next to the 32 packed P words, which
@@ -447,6 +523,10 @@ flash_fwd_kernel_sm100_p4(const __grid_constant__ CUtensorMap tmQ, const __grid_
             const float l_tot = l_run + l_peer;
             const bool row_empty = (m_ref == -INFINITY) || !(l_tot > 0.f);   // no visible key: O = 0, LSE = 0
             const float inv_l = row_empty ? 0.f : (1.f / l_tot);
+#if FA_P4_STAGING2
+            if (nstore > 0) mbar_wait(&bar_stage_free[t], (nstore - 1) & 1);   // the previous store of this slot has read the tile
+            uint8_t* sStageT = sStage + t * L::kTile;
+#else
             if (hh == 0 && wq == 0) {    // take the staging tile (the other tile's epilogue may hold it); the whole warp spins
                 int got;                 // together: bar.sync below is warp-aligned
                 do {
@@ -457,7 +537,10 @@ flash_fwd_kernel_sm100_p4(const __grid_constant__ CUtensorMap tmQ, const __grid_
                 } while (!got);
             }
             named_bar_sync(tile_bar, 2 * kBlockM);
-            const uint32_t stage = smem_u32(sStage) + hh * L::kSlab;
+            uint8_t* sStageT = sStage;
+#endif
+            if (r_in_tile == 0 && hh == 0) FA_TRACE_EVENT(t, its - 1, 1);
+            const uint32_t stage = smem_u32(sStageT) + hh * L::kSlab;
 #pragma unroll
             for (int c = 0; c < 2; ++c) {
                 uint32_t o[32];
@@ -480,13 +563,23 @@ flash_fwd_kernel_sm100_p4(const __grid_constant__ CUtensorMap tmQ, const __grid_
             }
             if (hh == 0 && row < g.sq_b) lse_row[row] = row_empty ? 0.f : (m_ref * p.scale + logf(l_tot));
             fence_proxy_async_smem();                          // generic-proxy writes -> visible to the TMA engine
-            named_bar_sync(tile_bar, 2 * kBlockM);
             const bool whole_tile = (mt + kBlockM <= g.sq_b) || (p.cu_q == nullptr);   // dense: TMA clips rows >= seqlen_q itself
+#if FA_P4_STAGING2
             if (whole_tile) {
-                if (hh == 0 && r_in_tile == 0) {
+                named_bar_arrive(11 + t, 2 * kBlockM + 32);    // hand the tile to helper warp 18 + t and move on
+                ++nstore;
+            } else {
+                named_bar_sync(tile_bar, 2 * kBlockM);
+            }
+#else
+            named_bar_sync(tile_bar, 2 * kBlockM);
+#endif
+            if (r_in_tile == 0 && hh == 0) FA_TRACE_EVENT(t, its - 1, 7);
+            if (whole_tile) {
+                if (!FA_P4_STAGING2 && hh == 0 && r_in_tile == 0) {
 #pragma unroll
                     for (int sl = 0; sl < kSlabs; ++sl)
-                        tma_store_4d(&tmO, sStage + sl * L::kSlab, sl * 64, w.bidh, g.q_row0 + mt, g.tma_b);
+                        tma_store_4d(&tmO, sStageT + sl * L::kSlab, sl * 64, w.bidh, g.q_row0 + mt, g.tma_b);
                     tma_store_commit();
                     tma_store_wait_read<0>();                  // staging tile has been read; global writes complete later
                     __threadfence_block();
@@ -496,7 +589,7 @@ flash_fwd_kernel_sm100_p4(const __grid_constant__ CUtensorMap tmQ, const __grid_
             } else {
                 // ragged varlen tail: a TMA box would spill into the next sequence -> predicated coalesced stores
                 constexpr int kChunksPerRow = D / 8;
-                const uint32_t stage0 = smem_u32(sStage);
+                const uint32_t stage0 = smem_u32(sStageT);
                 for (int idx = hh * kBlockM + r_in_tile; idx < kBlockM * kChunksPerRow; idx += 2 * kBlockM) {
                     const int rr = idx / kChunksPerRow, ch = idx % kChunksPerRow;
                     if (mt + rr < g.sq_b) {
@@ -505,13 +598,13 @@ flash_fwd_kernel_sm100_p4(const __grid_constant__ CUtensorMap tmQ, const __grid_
                     }
                 }
                 named_bar_sync(tile_bar, 2 * kBlockM);
-                if (hh == 0 && r_in_tile == 0) atomicExch(stage_lock, 0);
+                if (!FA_P4_STAGING2 && hh == 0 && r_in_tile == 0) atomicExch(stage_lock, 0);
                 __syncwarp();
             }
             if (r_in_tile == 0 && hh == 0) FA_TRACE_EVENT(t, its - 1, 6);
             ++nitem;
         }
-        if (hh == 0 && r_in_tile == 0) tma_store_wait<0>();   // all bulk stores of this thread have landed before the CTA retires
+        if (!FA_P4_STAGING2 && hh == 0 && r_in_tile == 0) tma_store_wait<0>();   // all bulk stores of this thread have landed before the CTA retires
     }
 
     tc_fence_before();

@@ -733,7 +733,7 @@ int launch_fwd_sm100(const fa_fwd_params* p, cudaStream_t stream) {
         for (int r = 0; r < 3; ++r)
             for (int j = 26; j < 40; ++j) {
                 printf("TRACE %d %2d :", r, j);
-                for (int e = 0; e < 7; ++e) printf(" %8lld", h[(r * 64 + j) * 8 + e] ? h[(r * 64 + j) * 8 + e] - t0 : -1LL);
+                for (int e = 0; e < 8; ++e) printf(" %8lld", h[(r * 64 + j) * 8 + e] ? h[(r * 64 + j) * 8 + e] - t0 : -1LL);
                 printf("\n");
             }
         fflush(stdout);
