@@ -315,7 +315,9 @@ flash_fwd_kernel_sm100_p4(const __grid_constant__ CUtensorMap tmQ, const __grid_
         const float inv_c2 = p.inv_scale_log2;
         int its = 0;       // S_t steps so far
         int nitem = 0;     // items with keys finished by this slot
-        int nstore = 0;    // FA_P4_STAGING2: TMA stores of this slot handed to the helper warp so far
+#if FA_P4_STAGING2
+        int nstore = 0;    // TMA stores of this slot handed to the helper warp so far
+#endif
 
         // The 64 scores of a thread are walked in four chunks of 16 columns (tcgen05.ld x16), the next chunk in flight
         // while the current one is processed: only 32 score registers are ever live next to the 32 packed P words, which
