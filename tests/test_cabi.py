@@ -59,6 +59,19 @@ def test_bwd_validates_gradient_pointers():
     assert rc == cabi.FA_ERR_INVALID_ARG and "dout" in lib.fa_b200_last_error().decode()
 
 
+def test_bwd_workspace_bytes_is_the_fused_backward_accumulator():
+    """host-only: the fp32 dQ accumulator [b][h][ceil64(seqlen_q)][d] for head_dim 128 (fused backward), nothing for 64"""
+    import os
+    lib = cabi.load()
+    if os.environ.get("FA_B200_BWD", "fused")[0] != "f":
+        pytest.skip("FA_B200_BWD selects a non-fused backward")
+    p = _params(b=3, seqlen_q=130, h=6, h_k=2, d=128)
+    assert lib.fa_b200_bwd_workspace_bytes(ctypes.byref(p)) == 3 * 6 * 192 * 128 * 4
+    p = _params(b=3, seqlen_q=130, h=6, h_k=2, d=64)
+    assert lib.fa_b200_bwd_workspace_bytes(ctypes.byref(p)) == 0
+    assert lib.fa_b200_bwd_workspace_bytes(None) == 0
+
+
 def test_struct_layout_matches_header():
     # 7 pointers + 8 int64 + 2 int32 = 128 bytes; bwd adds 6 pointers
     assert ctypes.sizeof(cabi.FwdParams) == 7 * 8 + 8 * 8 + 2 * 4
