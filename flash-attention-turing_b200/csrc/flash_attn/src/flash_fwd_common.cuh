@@ -82,8 +82,10 @@ FA_DEVICE void softmax_step(float (&s)[kBlockN], const bool first, const float c
             const float2 x = __ffma2_rn(make_float2(a, b), c2v, negv);
             return make_float2(fast_exp2(x.x), fast_exp2(x.y));
         }
-        const float s_floor = (-125.f - negx) * inv_c2;  // clamp so that 2^x stays a normal float
-        const float2 x = __ffma2_rn(make_float2(fmaxf(a, s_floor), fmaxf(b, s_floor)), c2v, negv);
+        // clamp so that 2^x stays a normal float (above 126 the exponent add below would wrap around; the speculative
+        // pass can see such arguments, the max vote then redoes the tile)
+        const float s_floor = (-125.f - negx) * inv_c2, s_ceil = (126.f - negx) * inv_c2;
+        const float2 x = __ffma2_rn(make_float2(fminf(fmaxf(a, s_floor), s_ceil), fminf(fmaxf(b, s_floor), s_ceil)), c2v, negv);
         const float2 tt = __fadd2_rn(x, magic);                   // low mantissa bits = rint(x)
         const float2 nnf = __ffma2_rn(tt, make_float2(-1.f, -1.f), magic);   // -rint(x), exact
         const float2 f = __fadd2_rn(x, nnf);                      // x - rint(x)  in [-0.5, 0.5]

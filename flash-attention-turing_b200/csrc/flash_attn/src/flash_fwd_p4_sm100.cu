@@ -334,8 +334,13 @@ flash_fwd_kernel_sm100_p4(const __grid_constant__ CUtensorMap tmQ, const __grid_
                 float2 pp;
                 if (((i * kEmu8) & 7) < kEmu8) {
                     const float2 magic = make_float2(12582912.f, 12582912.f);       // 1.5 * 2^23
-                    const float s_floor = (-125.f - neg) * inv_c2;                  // keeps the emulated 2^x a normal float
-                    const float2 x = __ffma2_rn(make_float2(fmaxf(s[2 * i], s_floor), fmaxf(s[2 * i + 1], s_floor)), c2v, negv);
+                    // Clamp the argument to [-125, 126]: below, the result would be subnormal; above, the exponent add
+                    // wraps around (2^141 came out as -2^-116, the tile-sum vote did not trip and a whole key tile was lost:
+                    // tests/test_parity_gpu.py::test_rescale_path_scores_growing_along_the_keys).  At 126 the emulated value
+                    // is ~2^126: the sum trips the vote exactly like the +inf of MUFU.EX2 does.
+                    const float s_floor = (-125.f - neg) * inv_c2, s_ceil = (126.f - neg) * inv_c2;
+                    const float2 x = __ffma2_rn(make_float2(fminf(fmaxf(s[2 * i], s_floor), s_ceil),
+                                                            fminf(fmaxf(s[2 * i + 1], s_floor), s_ceil)), c2v, negv);
                     const float2 tt = __fadd2_rn(x, magic);                                   // low mantissa bits = rint(x)
                     const float2 nnf = __ffma2_rn(tt, make_float2(-1.f, -1.f), magic);        // -rint(x), exact
                     const float2 f = __fadd2_rn(x, nnf);                                      // x - rint(x) in [-0.5, 0.5]

@@ -198,6 +198,42 @@ def test_full_size_properties(name, b, s, causal):
         assert torch.equal(o4[:, : s // 2], o[:1, : s // 2]) and torch.equal(l4[:, :, : s // 2], lse[:1, :, : s // 2])
 
 
+@pytest.mark.parametrize("d", [64, 128])
+@pytest.mark.parametrize("causal", [False, True])
+@pytest.mark.parametrize("dtype", ["fp16", "bf16"])
+def test_rescale_path_scores_growing_along_the_keys(d, causal, dtype):
+    """The forward keeps a lazily updated reference max (it only moves when a key tile's exponentials would leave the
+    2^9 range).  Random inputs almost never move it after the first tile, so this case makes every 128-key tile ~20
+    exponent units larger than the one before: the rescale path (true max, exchange between the two threads of a row,
+    O / l rescale, exponentials redone) runs at every step, and one row in this draw jumps by 2^141 inside one tile
+    (its speculative exponentials overflow).  That row exposed a real bug on the B200: the polynomial exp2 wrapped
+    around for arguments > 128 and the tile-sum vote did not trip, so a whole key tile was dropped (O off by ~3, LSE
+    by 68.7; profiles/r01s2_rescale_bug.log).  The inputs are ill-conditioned (softmax nearly one-hot, |k| up to ~170),
+    so the gates here are absolute and wide — measured errors on the fixed kernel: bf16 O max 1.8e-2 / mean 4e-3,
+    LSE 1e-4 — but a dropped or mis-scaled tile is an O(1) error."""
+    dt = DT[dtype]
+    torch.manual_seed(7)
+    b, sq, sk, h, hk = 2, 300, 1024, 4, 2
+    q = torch.randn(b, sq, h, d, device="cuda", dtype=dt)
+    k = torch.randn(b, sk, hk, d, device="cuda", dtype=dt)
+    v = torch.randn(b, sk, hk, d, device="cuda", dtype=dt)
+    grow = (1.0 + 6.0 * (torch.arange(sk, device="cuda") // 128)).to(dt)      # 1, 7, 13, ... per key tile
+    k = (k * grow[None, :, None, None]).contiguous()
+
+    def check(kk, what):
+        o, lse = cabi.fwd(q, kk, v, causal)
+        ro, rl = attention_ref(q, kk, v, causal)
+        assert torch.isfinite(o.float()).all() and torch.isfinite(lse).all(), what
+        m = error_metrics(o, ro)
+        assert m["max_abs"] <= 0.25 * max(1.0, m["ref_max"] / 4.0), f"{what}: O {m}"
+        assert m["mean_abs"] <= 2e-2, f"{what}: O {m}"
+        lerr = (lse - rl).abs().max().item()
+        assert lerr <= 0.05 * max(1.0, rl.abs().max().item() / 8.0), f"{what}: LSE max err {lerr}"
+
+    check(k, "growing")
+    check(torch.flip(k, dims=[1]).contiguous(), "shrinking")   # reference set by the first tile, never moves again
+
+
 def test_full_size_backward_c4_slice():
     """C4 is b4 s16384 fwd+bwd; the backward is checked on a (batch, head) slice at s=2048 against fp32 autograd.
     dK and dV must be bit-identical between two runs.  dQ of the default (fused) backward is accumulated with fp32
