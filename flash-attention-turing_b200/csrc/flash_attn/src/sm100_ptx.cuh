@@ -280,10 +280,11 @@ FA_DEVICE float fast_exp2(float x) {
 }
 // 2^x for a pair of floats on the FMA pipe (no MUFU): Cody-Waite split x = n + f, f in [-0.5, 0.5], degree-3 minimax
 // polynomial for 2^f (|rel err| < 7.5e-5, far below 16-bit rounding), exponent inserted with an integer add.
-// x is clamped to >= -125 (NaN / -inf -> 2^-125, i.e. zero after any 16-bit rounding); x must stay below 128.
+// x is clamped to [-125, 126] (NaN / -inf -> 2^-125, i.e. zero after any 16-bit rounding; above 126 the exponent add
+// would wrap around).
 FA_DEVICE float2 exp2_poly_pair(float2 x) {
     const float2 magic = make_float2(12582912.f, 12582912.f);                 // 1.5 * 2^23: low mantissa bits of x + magic = rint(x)
-    x = make_float2(fmaxf(x.x, -125.f), fmaxf(x.y, -125.f));
+    x = make_float2(fminf(fmaxf(x.x, -125.f), 126.f), fminf(fmaxf(x.y, -125.f), 126.f));
     const float2 tt = __fadd2_rn(x, magic);
     const float2 nnf = __ffma2_rn(tt, make_float2(-1.f, -1.f), magic);        // -rint(x), exact
     const float2 f = __fadd2_rn(x, nnf);
