@@ -1,0 +1,104 @@
+"""CPU restatement of the device-side index logic that decides WHICH tile a CTA works on — a wrong formula there silently
+drops or duplicates tiles.  Mirrors (line for line, in Python integers):
+  * decode_item / make_tile_sched   (flash_fwd_common.cuh): the persistent forward's static work list
+  * item_geom's per-tile key-block counts vs the element-wise causal rule j - i <= sk - sq (mask.h:20-72 in the reference)
+  * the fused backward's rotated walk over the 64-row query sub-tiles (flash_bwd_tc_sm100.cu: it0, steps_per_head, rot, q_sub)
+"""
+import itertools
+import random
+
+
+def make_tile_sched(b, h, sq, sk, d, group_mb=16):
+    num_mblk = (sq + 255) // 256
+    bh = b * h
+    kv_bytes_per_head = 2 * sk * d * 2
+    grp = (group_mb << 20) // kv_bytes_per_head if kv_bytes_per_head > 0 else bh
+    grp = max(1, min(grp, bh))
+    return {"num_mblk": num_mblk, "bh": bh, "group": grp, "total": num_mblk * bh}
+
+
+def decode_item(ts, n, h, causal):
+    per_group = ts["group"] * ts["num_mblk"]
+    g = n // per_group
+    r = n - g * per_group
+    heads_here = min(ts["group"], ts["bh"] - g * ts["group"])
+    level = r // heads_here
+    head_local = r - level * heads_here
+    bhi = g * ts["group"] + head_local
+    mblk = (ts["num_mblk"] - 1 - level) if causal else level
+    return mblk, bhi % h, bhi // h
+
+
+def test_forward_work_list_covers_every_tile_pair_exactly_once():
+    random.seed(0)
+    shapes = [(4, 32, 4096, 4096, 128), (4, 32, 8192, 8192, 128), (1, 1, 1, 1, 128), (3, 6, 129, 127, 64),
+              (2, 4, 1025, 1, 128), (256, 32, 16384, 16384, 128)]
+    shapes += [(random.randint(1, 9), random.randint(1, 33), random.randint(1, 5000), random.randint(1, 70000),
+                random.choice([64, 128])) for _ in range(200)]
+    for (b, h, sq, sk, d), causal, mb in itertools.product(shapes, (False, True), (1, 16, 4096)):
+        if b * h * ((sq + 255) // 256) > 300000:
+            b = 2                                   # keep the enumeration small; the formulas do not depend on b's size
+        ts = make_tile_sched(b, h, sq, sk, d, mb)
+        seen = set()
+        for n in range(ts["total"]):
+            item = decode_item(ts, n, h, causal)
+            mblk, bidh, bidb = item
+            assert 0 <= mblk < ts["num_mblk"] and 0 <= bidh < h and 0 <= bidb < b, (item, ts)
+            assert item not in seen, f"duplicate {item} for {(b, h, sq, sk, d, causal, mb)}"
+            seen.add(item)
+        assert len(seen) == ts["num_mblk"] * b * h
+
+
+def nblk(mt, sq_b, sk_b, causal):
+    """item_geom: key blocks a 128-row query tile starting at row mt has to visit"""
+    kv_end = sk_b if mt < sq_b else 0
+    if causal:
+        kv_end = min(kv_end, max(0, mt + 128 + (sk_b - sq_b)))
+    return (kv_end + 127) // 128
+
+
+def test_key_block_counts_agree_with_the_elementwise_causal_rule():
+    random.seed(1)
+    cases = [(1, 1), (63, 65), (65, 63), (128, 128), (129, 127), (1023, 1025), (1025, 1023), (1, 1025), (1025, 1), (300, 1024)]
+    cases += [(random.randint(1, 1500), random.randint(1, 1500)) for _ in range(150)]
+    for (sq, sk), causal in itertools.product(cases, (False, True)):
+        off = sk - sq
+        for mt in range(0, sq, 128):
+            rows = range(mt, min(mt + 128, sq))
+            last_visible = max((min(sk - 1, i + off) if causal else sk - 1) for i in rows)   # -1 or less: nothing visible
+            need = 0 if last_visible < 0 else last_visible // 128 + 1
+            assert nblk(mt, sq, sk, causal) == need, (sq, sk, causal, mt)
+
+
+def fused_bwd_steps(n0, sq_b, sk_b, causal, block_x):
+    """query sub-tiles (64 rows) the fused backward's CTA for key tile n0 walks, in its rotated order"""
+    off = sk_b - sq_b
+    i_first = max(0, n0 - off) if causal else 0
+    it0 = i_first // 64
+    nsub = (sq_b + 63) // 64
+    steps = max(0, nsub - it0)
+    rot = (block_x * 2) % steps if steps > 0 else 0
+    order = []
+    for st in range(steps):
+        ls = st % steps + rot
+        if ls >= steps:
+            ls -= steps
+        order.append(it0 + ls)
+    return order
+
+
+def test_fused_backward_walk_visits_every_visible_query_sub_tile_once():
+    random.seed(2)
+    cases = [(4096, 4096), (300, 1024), (1025, 1023), (1, 1), (65, 63), (129, 127), (1, 1025), (1025, 1)]
+    cases += [(random.randint(1, 3000), random.randint(1, 3000)) for _ in range(100)]
+    for (sq, sk), causal in itertools.product(cases, (False, True)):
+        off = sk - sq
+        for bx, n0 in enumerate(range(0, sk, 128)):
+            order = fused_bwd_steps(n0, sq, sk, causal, bx)
+            assert len(order) == len(set(order))
+            # every sub-tile that holds a query row able to see a key of this tile must be walked
+            keys = range(n0, min(n0 + 128, sk))
+            for it in range((sq + 63) // 64):
+                rows = range(it * 64, min(it * 64 + 64, sq))
+                visible = any((not causal) or (keys[0] <= i + off) for i in rows)
+                assert (it in order) or not visible, (sq, sk, causal, n0, it)
