@@ -102,3 +102,56 @@ def test_fused_backward_walk_visits_every_visible_query_sub_tile_once():
                 rows = range(it * 64, min(it * 64 + 64, sq))
                 visible = any((not causal) or (keys[0] <= i + off) for i in rows)
                 assert (it in order) or not visible, (sq, sk, causal, n0, it)
+
+
+def test_backward_causal_predicates_agree_with_the_elementwise_rule():
+    """flash_bwd_tc_sm100.cu, dK/dV-type kernels: thread (g, r) owns key row jg = n0 + r and query columns 32g..32g+31 of the
+    64-row sub-tile `it`; it zeroes P where `need_mask && column < cmin`.  Truth: key j is visible to query i iff j <= i + off."""
+    random.seed(3)
+    cases = [(300, 1024), (1025, 1023), (65, 63), (129, 127), (128, 128), (1, 1025), (1025, 1), (640, 640)]
+    cases += [(random.randint(1, 700), random.randint(1, 700)) for _ in range(40)]
+    for sq, sk in cases:
+        off = sk - sq
+        for bx, n0 in enumerate(range(0, sk, 128)):
+            for it in fused_bwd_steps(n0, sq, sk, True, bx):
+                need_mask = it * 64 < n0 + 128 - 1 - off
+                for r in (0, 1, 31, 63, 64, 127):
+                    jg = n0 + r
+                    if jg >= sk:
+                        continue
+                    for g in (0, 1):
+                        cmin = (jg - off - it * 64 - g * 32) if need_mask else 0
+                        for c in range(32):
+                            i = it * 64 + g * 32 + c
+                            if i >= sq:
+                                continue
+                            kernel_zeroes = need_mask and c < cmin
+                            assert kernel_zeroes == (jg > i + off), (sq, sk, n0, it, r, g, c)
+            # sub-tiles the walk skips hold no query row that sees a key of this tile
+            walked = set(fused_bwd_steps(n0, sq, sk, True, bx))
+            for it in range((sq + 63) // 64):
+                if it not in walked:
+                    assert all(n0 > i + off for i in range(it * 64, min(it * 64 + 64, sq)))
+
+
+def test_dq_kernel_key_ranges_and_mask_agree_with_the_elementwise_rule():
+    """flash_bwd_dq_kernel_sm100 / forward: a 128-row query tile at m0 visits ceil(min(sk, m0 + 128 + off) / 128) key tiles and
+    masks column c of key tile n0 for row `row` iff c > min(sk - 1, row + off) - n0 (only on tiles flagged need_mask)."""
+    random.seed(4)
+    cases = [(300, 1024), (1025, 1023), (65, 63), (129, 127), (1, 1025), (1025, 1)] + [(random.randint(1, 600), random.randint(1, 600)) for _ in range(40)]
+    for (sq, sk), causal in itertools.product(cases, (False, True)):
+        off = sk - sq
+        for m0 in range(0, sq, 128):
+            nb = nblk(m0, sq, sk, causal)
+            for row in {m0, min(m0 + 127, sq - 1), min(m0 + 64, sq - 1)}:
+                col_limit = min(sk - 1, row + off) if causal else sk - 1
+                for j in range(nb):
+                    n0 = j * 128
+                    need_mask = (n0 + 128 > sk) or (causal and (n0 + 128 - 1 > m0 + off))
+                    for c in (0, 1, 63, 64, 127):
+                        key = n0 + c
+                        truth_visible = key < sk and ((not causal) or key <= row + off)
+                        kernel_visible = not (need_mask and c > col_limit - n0)
+                        assert kernel_visible == truth_visible, (sq, sk, causal, m0, row, j, c)
+                # nothing visible beyond the visited tiles
+                assert all(not (k < sk and ((not causal) or k <= row + off)) for k in range(nb * 128, min(sk, nb * 128 + 256)))
