@@ -63,22 +63,39 @@ int encode_tmap_4d(CUtensorMap* out, const void* base, bool bf16, const uint64_t
     return FA_OK;
 }
 
-static int check_device() {
-    static int cached = -1;  // 1 ok, 0 bad
-    if (cached < 0) {
-        int dev = 0, major = 0;
-        if (cudaGetDevice(&dev) != cudaSuccess ||
-            cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) {
-            set_error("no CUDA device");
-            return FA_ERR_NO_DEVICE;
-        }
-        cached = (major == 10) ? 1 : 0;
-    }
-    if (!cached) {
-        set_error("libfa_b200 needs an sm_100 (Blackwell B200) device; there is no fallback path");
+int current_device_info(const DeviceInfo** out) {
+    constexpr int kMaxDev = 64;
+    static DeviceInfo table[kMaxDev];
+    static std::atomic<int> ready[kMaxDev];          // 0 unknown, 1 filled (zero-initialised)
+    static thread_local DeviceInfo overflow;         // ordinals >= kMaxDev: queried on every call
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) {
+        set_error("no CUDA device");
         return FA_ERR_NO_DEVICE;
     }
+    DeviceInfo* di = (dev >= 0 && dev < kMaxDev) ? &table[dev] : &overflow;
+    if (dev < 0 || dev >= kMaxDev || ready[dev].load(std::memory_order_acquire) == 0) {
+        DeviceInfo tmp;
+        tmp.ordinal = dev;
+        if (cudaDeviceGetAttribute(&tmp.cc_major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess ||
+            cudaDeviceGetAttribute(&tmp.num_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) {
+            set_error("cannot query device %d", dev);
+            return FA_ERR_CUDA;
+        }
+        *di = tmp;                                    // racing threads write identical values
+        if (dev >= 0 && dev < kMaxDev) ready[dev].store(1, std::memory_order_release);
+    }
+    if (di->cc_major != 10) {
+        set_error("libfa_b200 needs an sm_100 (Blackwell B200) device, device %d is sm_%d0; there is no fallback path", dev, di->cc_major);
+        return FA_ERR_NO_DEVICE;
+    }
+    *out = di;
     return FA_OK;
+}
+
+static int check_device() {
+    const DeviceInfo* di = nullptr;
+    return current_device_info(&di);
 }
 
 static int validate_fwd(const fa_fwd_params* p) {
@@ -97,6 +114,10 @@ static int validate_fwd(const fa_fwd_params* p) {
         p->total_q > INT32_MAX || p->total_k > INT32_MAX) {
         set_error("size out of range"); return FA_ERR_INVALID_ARG;
     }
+    // the device-side work lists index (256-row query block, batch, head) triples and (batch * head) pairs with 32 bits
+    if (p->b * p->h > INT32_MAX / 2 || ((p->seqlen_q + 63) / 64) * p->b * p->h > INT32_MAX) {
+        set_error("batch * heads * query blocks exceeds the 32-bit work list"); return FA_ERR_INVALID_ARG;
+    }
     if ((reinterpret_cast<uintptr_t>(p->q) | reinterpret_cast<uintptr_t>(p->k) | reinterpret_cast<uintptr_t>(p->v) |
          reinterpret_cast<uintptr_t>(p->o)) & 15) {
         set_error("q/k/v/o must be 16-byte aligned"); return FA_ERR_INVALID_ARG;
@@ -104,9 +125,27 @@ static int validate_fwd(const fa_fwd_params* p) {
     return FA_OK;
 }
 
+#ifdef FA_TRACE
+static long long* g_trace = nullptr;
+constexpr size_t kTraceWords = 6 * 64 * 8;
+long long* fa_trace_buffer(cudaStream_t stream) {
+    if (!g_trace && cudaMalloc(&g_trace, kTraceWords * sizeof(long long)) != cudaSuccess) return nullptr;
+    cudaMemsetAsync(g_trace, 0, kTraceWords * sizeof(long long), stream);
+    return g_trace;
+}
+#endif
+
 }  // namespace fa100
 
 using namespace fa100;
+
+#ifdef FA_TRACE
+extern "C" int fa_b200_trace_read(long long* host, int words) {   // trace builds only; not part of include/fa_b200.h
+    if (!g_trace || words > (int)kTraceWords) return -1;
+    cudaDeviceSynchronize();
+    return cudaMemcpy(host, g_trace, (size_t)words * sizeof(long long), cudaMemcpyDeviceToHost) == cudaSuccess ? 0 : -1;
+}
+#endif
 
 extern "C" {
 

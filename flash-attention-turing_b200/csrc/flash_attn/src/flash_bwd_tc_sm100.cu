@@ -22,6 +22,8 @@
 #include <math.h>
 #include <stdlib.h>
 
+#include <atomic>
+
 #include "fa_common.h"
 #include "flash_bwd_params.h"
 #include "sm100_ptx.cuh"
@@ -43,6 +45,8 @@ FA_DEVICE SeqGeom seq_geom(const BwdParams& p, int bidb) {
     if (p.cu_q != nullptr) {
         g.q_row0 = p.cu_q[bidb]; g.sq_b = p.cu_q[bidb + 1] - g.q_row0;
         g.k_row0 = p.cu_k[bidb]; g.sk_b = p.cu_k[bidb + 1] - g.k_row0;
+        // LSE / dsum rows and the fused dQ accumulator are sized by max_seqlen_q: never index past them
+        g.sq_b = max(0, min(g.sq_b, p.sq)); g.sk_b = max(0, min(g.sk_b, p.sk));
         g.tma_b = 0;
     } else {
         g.q_row0 = 0; g.k_row0 = 0; g.sq_b = p.sq; g.sk_b = p.sk; g.tma_b = bidb;
@@ -1106,7 +1110,7 @@ flash_bwd_dq_kernel_sm100_convert(const BwdParams p) {
     const int bidb = blockIdx.z, bidh = blockIdx.y;
     const int i = blockIdx.x * 16 + (threadIdx.x >> 4), ch = threadIdx.x & 15;
     int q_row0 = 0, sq_b = p.sq;
-    if (p.cu_q) { q_row0 = p.cu_q[bidb]; sq_b = p.cu_q[bidb + 1] - q_row0; }
+    if (p.cu_q) { q_row0 = p.cu_q[bidb]; sq_b = min(p.cu_q[bidb + 1] - q_row0, p.sq); }
     if (i >= sq_b) return;
     const int64_t row_base = p.cu_q ? (int64_t)q_row0 : (int64_t)bidb * p.sq;
     const int64_t eoff = (((int64_t)bidb * p.h + bidh) * p.sq_pad + i) * D + 8 * ch;
@@ -1132,7 +1136,6 @@ flash_bwd_dq_kernel_sm100_convert(const BwdParams p) {
 template <int D, bool kBf16>
 static int launch_tc(const BwdParams& kp, const CUtensorMap& tq128, const CUtensorMap& tdo128, const CUtensorMap& tq64,
                      const CUtensorMap& tdo64, const CUtensorMap& tk, const CUtensorMap& tv, cudaStream_t stream) {
-    static bool attr_set = false;
     // FA_B200_BWD_EMU=1: polynomial exponentials for 2 of 8 column pairs in the dQ kernel.  Measured: the elementwise phase
     // drops from 1300 to 960 cycles per step, but the kernel is then bound by its MMA issue loop (1770 cycles per step
     // either way; 2.89 vs 2.85 ms for the whole backward at C2) -> off by default, MUFU.EX2 everywhere.
@@ -1140,62 +1143,21 @@ static int launch_tc(const BwdParams& kp, const CUtensorMap& tq128, const CUtens
     if (dq_emu < 0) { const char* e = getenv("FA_B200_BWD_EMU"); dq_emu = e ? (atoi(e) != 0) : 0; }
     auto kdq = dq_emu ? flash_bwd_dq_kernel_sm100<D, kBf16, true> : flash_bwd_dq_kernel_sm100<D, kBf16, false>;
     auto kkv = flash_bwd_dk_dv_kernel_sm100<D, kBf16>;
-    if (!attr_set) {
-        FA_CUDA_CHECK(cudaFuncSetAttribute(flash_bwd_dq_kernel_sm100<D, kBf16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, DqSmem<D>::kBytes));
-        FA_CUDA_CHECK(cudaFuncSetAttribute(flash_bwd_dq_kernel_sm100<D, kBf16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, DqSmem<D>::kBytes));
-        FA_CUDA_CHECK(cudaFuncSetAttribute(kkv, cudaFuncAttributeMaxDynamicSharedMemorySize, DkvSmem<D>::kBytes));
-        attr_set = true;
-    }
+    const DeviceInfo* di = nullptr;
+    int rc = current_device_info(&di);
+    if (rc != FA_OK) return rc;
+    static std::atomic<unsigned long long> m_dq1{0}, m_dq0{0}, m_kv{0};   // per device, see ensure_dynamic_smem
+    if ((rc = ensure_dynamic_smem(flash_bwd_dq_kernel_sm100<D, kBf16, true>, DqSmem<D>::kBytes, m_dq1, di->ordinal)) != FA_OK) return rc;
+    if ((rc = ensure_dynamic_smem(flash_bwd_dq_kernel_sm100<D, kBf16, false>, DqSmem<D>::kBytes, m_dq0, di->ordinal)) != FA_OK) return rc;
+    if ((rc = ensure_dynamic_smem(kkv, DkvSmem<D>::kBytes, m_kv, di->ordinal)) != FA_OK) return rc;
     if (kp.sq > 0) {
         dim3 g((kp.sq + kBM - 1) / kBM, kp.h, kp.b);
-#ifdef FA_TRACE
-        if (getenv("FA_B200_TRACE")) {
-            BwdParams kt = kp;
-            static long long* d_trace = nullptr;
-            if (!d_trace) cudaMalloc(&d_trace, 2 * 64 * 8 * sizeof(long long));
-            cudaMemsetAsync(d_trace, 0, 2 * 64 * 8 * sizeof(long long), stream);
-            kt.trace = d_trace;
-            kdq<<<g, 384, DqSmem<D>::kBytes, stream>>>(tq128, tdo128, tk, tv, kt);
-            cudaStreamSynchronize(stream);
-            static long long hh[2 * 64 * 8];
-            cudaMemcpy(hh, d_trace, sizeof(hh), cudaMemcpyDeviceToHost);
-            const long long t0 = hh[0];
-            for (int r = 0; r < 2; ++r)
-                for (int j = 0; j < 10; ++j) {
-                    printf("BTRACE dq %d %2d :", r, j);
-                    for (int e = 0; e < 5; ++e) printf(" %8lld", hh[(r * 64 + j) * 8 + e] ? hh[(r * 64 + j) * 8 + e] - t0 : -1LL);
-                    printf("\n");
-                }
-            fflush(stdout);
-        } else
-#endif
         kdq<<<g, 384, DqSmem<D>::kBytes, stream>>>(tq128, tdo128, tk, tv, kp);
         FA_CUDA_CHECK(cudaGetLastError());
         count_launch();
     }
     if (kp.sk > 0) {
         dim3 g((kp.sk + kBM - 1) / kBM, kp.h_k, kp.b);
-#ifdef FA_TRACE
-        if (getenv("FA_B200_TRACE")) {
-            BwdParams kt = kp;
-            static long long* d_trace2 = nullptr;
-            if (!d_trace2) cudaMalloc(&d_trace2, 2 * 64 * 8 * sizeof(long long));
-            cudaMemsetAsync(d_trace2, 0, 2 * 64 * 8 * sizeof(long long), stream);
-            kt.trace = d_trace2;
-            kkv<<<g, 384, DkvSmem<D>::kBytes, stream>>>(tq64, tdo64, tk, tv, kt);
-            cudaStreamSynchronize(stream);
-            static long long hh[2 * 64 * 8];
-            cudaMemcpy(hh, d_trace2, sizeof(hh), cudaMemcpyDeviceToHost);
-            const long long t0 = hh[0];
-            for (int r = 0; r < 2; ++r)
-                for (int j = 0; j < 10; ++j) {
-                    printf("BTRACE dkdv %d %2d :", r, j);
-                    for (int e = 0; e < 6; ++e) printf(" %8lld", hh[(r * 64 + j) * 8 + e] ? hh[(r * 64 + j) * 8 + e] - t0 : -1LL);
-                    printf("\n");
-                }
-            fflush(stdout);
-        } else
-#endif
         kkv<<<g, 384, DkvSmem<D>::kBytes, stream>>>(tq64, tdo64, tk, tv, kp);
         FA_CUDA_CHECK(cudaGetLastError());
         count_launch();
@@ -1223,35 +1185,14 @@ template <bool kBf16, bool kAcc16>
 static int launch_fused(const BwdParams& kp, const CUtensorMap& tq64, const CUtensorMap& tdo64, const CUtensorMap& tk,
                         const CUtensorMap& tv, cudaStream_t stream) {
     constexpr int D = 128;
-    static bool attr_set = false;
     auto kern = flash_bwd_dk_dv_kernel_sm100_fused<D, kBf16, kAcc16>;
-    if (!attr_set) {
-        FA_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, FzSmem<D>::kBytes));
-        attr_set = true;
-    }
+    const DeviceInfo* di = nullptr;
+    int rc = current_device_info(&di);
+    if (rc != FA_OK) return rc;
+    static std::atomic<unsigned long long> attr_mask{0};
+    if ((rc = ensure_dynamic_smem(kern, FzSmem<D>::kBytes, attr_mask, di->ordinal)) != FA_OK) return rc;
     FA_CUDA_CHECK(cudaMemsetAsync(kp.dqacc, 0, (size_t)bwd_fused_workspace_bytes(kp.b, kp.sq, kp.h, D) / (kAcc16 ? 2 : 1), stream));
     dim3 g((kp.sk + kBM - 1) / kBM, kp.h_k, kp.b);
-#ifdef FA_TRACE
-    if (getenv("FA_B200_TRACE")) {
-        BwdParams kt = kp;
-        static long long* d_trace = nullptr;
-        if (!d_trace) cudaMalloc(&d_trace, 2 * 64 * 8 * sizeof(long long));
-        cudaMemsetAsync(d_trace, 0, 2 * 64 * 8 * sizeof(long long), stream);
-        kt.trace = d_trace;
-        kern<<<g, 512, FzSmem<D>::kBytes, stream>>>(tq64, tdo64, tk, tv, kt);
-        cudaStreamSynchronize(stream);
-        static long long hh[2 * 64 * 8];
-        cudaMemcpy(hh, d_trace, sizeof(hh), cudaMemcpyDeviceToHost);
-        const long long t0 = hh[0];
-        for (int r = 0; r < 2; ++r)
-            for (int j = 0; j < 10; ++j) {
-                printf("BTRACE fused %d %2d :", r, j);
-                for (int e = 0; e < 8; ++e) printf(" %8lld", hh[(r * 64 + j) * 8 + e] ? hh[(r * 64 + j) * 8 + e] - t0 : -1LL);
-                printf("\n");
-            }
-        fflush(stdout);
-    } else
-#endif
     kern<<<g, 512, FzSmem<D>::kBytes, stream>>>(tq64, tdo64, tk, tv, kp);
     FA_CUDA_CHECK(cudaGetLastError());
     count_launch();
@@ -1268,7 +1209,7 @@ int launch_bwd_tc_sm100(const BwdParams& kp, bool bf16, cudaStream_t stream) {
     const uint64_t rows_q = varlen ? (uint64_t)kp.total_q : (uint64_t)kp.sq;
     const uint64_t rows_k = varlen ? (uint64_t)kp.total_k : (uint64_t)kp.sk;
     const uint64_t nb = varlen ? 1 : (uint64_t)kp.b;
-    if (rows_q == 0 || rows_k == 0) return -1;   // degenerate: let the row kernels write the zeros
+    if (rows_q == 0 || rows_k == 0) return -1;   // degenerate: the caller zero-fills the gradients
     CUtensorMap tq128, tdo128, tq64, tdo64, tk, tv;
     const uint32_t box128[4] = {64, 1, 128, 1}, box64[4] = {64, 1, 64, 1};
     {

@@ -44,6 +44,8 @@ class HostForward:
         self._key = None
         self._bufs = []
         self._free = []      # per slot: event recorded on the compute stream once the slot's inputs have been consumed
+        self._scratch = None  # copy_only: device o / lse stand-ins for the D2H leg
+        self.last_chunks = 0  # kernel launches (= chunks) of the last call
 
     def _ensure(self, key, chunk_b, q, k):
         if self._key == key:
@@ -57,10 +59,11 @@ class HostForward:
 
     def __call__(self, q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, is_causal: bool,
                  out: Optional[torch.Tensor] = None, lse: Optional[torch.Tensor] = None, chunks: Optional[int] = None,
-                 sync: bool = True) -> Tuple[torch.Tensor, torch.Tensor]:
+                 sync: bool = True, copy_only: bool = False) -> Tuple[torch.Tensor, torch.Tensor]:
         """q [b,sq,h,d], k/v [b,sk,h_k,d] on the host (pinned memory makes the copies asynchronous).  Returns (o, lse)
         as host tensors (`out` / `lse` if given, else new pinned tensors).  With sync=False the caller must synchronize
-        the current stream before reading them."""
+        the current stream before reading them.  copy_only=True moves the same bytes in the same chunks but launches no
+        kernel (the outputs are garbage): bench.py uses it to measure the copy floor of this host."""
         if q.is_cuda or k.is_cuda or v.is_cuda:
             raise ValueError("fwd_host expects host tensors; use flash_attn_turing.fwd for CUDA tensors")
         if q.dim() != 4 or k.shape != v.shape or k.dim() != 4 or q.shape[0] != k.shape[0]:
@@ -90,7 +93,12 @@ class HostForward:
                 up = torch.cuda.Event()
                 up.record(self.s_h2d)
             cur.wait_event(up)
-            o_c, l_c = self.fwd_fn(dq, dk, dv, is_causal)      # one kernel launch on the current stream
+            if copy_only:
+                if self._scratch is None or self._scratch[0].shape[0] < e - s or self._scratch[0].shape[1:] != dq.shape[1:]:
+                    self._scratch = (torch.empty_like(self._bufs[0][0]), torch.empty((chunk_b, h, sq), dtype=torch.float32, device=self.device))
+                o_c, l_c = self._scratch[0][: e - s], self._scratch[1][: e - s]
+            else:
+                o_c, l_c = self.fwd_fn(dq, dk, dv, is_causal)      # one kernel launch on the current stream
             ev = torch.cuda.Event()
             ev.record(cur)
             self._free[slot] = ev
@@ -102,6 +110,7 @@ class HostForward:
                 lse[s:e].copy_(l_c, non_blocking=True)
                 done = torch.cuda.Event()
                 done.record(self.s_d2h)
+        self.last_chunks = len(ranges)
         cur.wait_event(done)                 # stream order: work queued after this call sees the results on the host
         if sync:
             cur.synchronize()

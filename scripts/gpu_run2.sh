@@ -1,0 +1,15 @@
+#!/bin/bash
+# round 2, GPU call 2: pipelined quarter hand-over, PASS1_WIDE variant, new full-size tests
+L=gpurun_out/r02_run2.log
+mkdir -p gpurun_out; : > $L
+for lib in flash-attention-turing_b200/flash_attn_turing/libfa_b200.so ab/wide/libfa_b200.so; do
+  echo "== A/B $lib" >> $L
+  FA_B200_LIB=$lib timeout 300 python scripts/ab_time.py --sustain 1 C2 C3 C4 D64a S1k >> $L 2>&1
+  FA_B200_LIB=$lib FA_B200_EMU=3 FA_TAG="$lib EMU=3" timeout 300 python scripts/ab_time.py C2 C3 D64a >> $L 2>&1
+done
+echo "== trace" >> $L
+FA_B200_LIB=ab/trace/libfa_b200.so timeout 120 python scripts/trace_fwd.py 4 4096 >> $L 2>&1
+FA_B200_LIB=ab/trace/libfa_b200.so FA_TRACE_STEPS=4,20 timeout 120 python scripts/trace_fwd.py 4 4096 64 >> $L 2>&1
+echo "== pytest gpu" >> $L
+timeout 1500 python -m pytest tests -m gpu -x -q 2>&1 | tail -25 >> $L
+tail -5 $L

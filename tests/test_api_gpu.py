@@ -207,3 +207,75 @@ def test_reference_own_test_file_sampled(fat):
         if ref_kernels is not None:
             # on identical inputs we must not fail the reference's own acceptance gates more often than its own kernels do
             assert fo <= fr + max(3, n // 12), (fn.__name__, n, fo, fr)
+
+
+def test_backward_cuda_graph_capture(fat):
+    """the backward (memset of the dQ accumulator + 3 kernels + per-call TMA descriptors) is capturable and replays"""
+    q, k, v, do = _rand(2, 1024, 1024, 4, 2, 128, torch.bfloat16, seed=3)
+    o, l = fat.fwd(q, k, v, True)
+    fat.bwd(q, k, v, o, l, do, True)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        dq, dk, dv = fat.bwd(q, k, v, o, l, do, True)
+    for _ in range(2):
+        g.replay()
+    torch.cuda.synchronize()
+    ref = attention_ref(q, k, v, True, do)
+    for name, x, r in zip(("dq", "dk", "dv"), (dq, dk, dv), ref[2:]):
+        assert_close(x, r, torch.bfloat16, f"{name} (graph replay)")
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs in one process")
+def test_second_device_in_the_same_process(fat):
+    """per-device launch state (MaxDynamicSharedMemorySize, SM count, capability check) — the first call on cuda:1 after
+    cuda:0 used to launch with > 48 KB of dynamic shared memory not opted in"""
+    outs = []
+    for dev in (0, 1, 0):
+        with torch.cuda.device(dev):
+            torch.manual_seed(21)
+            q, k, v, do = (t.to(f"cuda:{dev}") for t in _rand(2, 300, 333, 4, 2, 128, torch.bfloat16, seed=21))
+            o, l = fat.fwd(q, k, v, True)
+            g = fat.bwd(q, k, v, o, l, do, True)
+            q64, k64, v64, do64 = (t[..., :64].contiguous() for t in (q, k, v, do))
+            o64, l64 = fat.fwd(q64, k64, v64, False)
+            g64 = fat.bwd(q64, k64, v64, o64, l64, do64, False)
+            torch.cuda.synchronize(dev)
+            ref = attention_ref(q, k, v, True, do)
+            for name, x, r in zip(("o", "dq", "dk", "dv"), (o, *g), (ref[0], *ref[2:])):
+                assert_close(x, r, torch.bfloat16, f"{name} on cuda:{dev}")
+            outs.append([t.cpu() for t in (o, l, g[1], g[2], o64, g64[2])])
+    for a, b_ in zip(outs[0], outs[1]):
+        assert torch.equal(a, b_), "cuda:0 and cuda:1 disagree on identical inputs"
+
+
+def test_concurrent_calls_from_two_threads(fat):
+    """two host threads, each on its own stream: launch state is per device and guarded, error text and launch counts are
+    thread-local (include/fa_b200.h)"""
+    import threading
+    q, k, v, do = _rand(2, 512, 640, 4, 2, 128, torch.bfloat16, seed=33)
+    o0, l0 = fat.fwd(q, k, v, True)
+    g0 = fat.bwd(q, k, v, o0, l0, do, True)
+    torch.cuda.synchronize()
+    res, errs = {}, []
+
+    def work(i):
+        try:
+            st = torch.cuda.Stream()
+            with torch.cuda.stream(st):
+                for _ in range(20):
+                    o, l = fat.fwd(q, k, v, True)
+                    g = fat.bwd(q, k, v, o, l, do, True)
+                    assert fat.last_launch_count() >= 3
+            st.synchronize()
+            res[i] = (o, l, g)
+        except Exception as e:  # noqa
+            errs.append(e)
+
+    th = [threading.Thread(target=work, args=(i,)) for i in range(2)]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    assert not errs, errs
+    for i in range(2):
+        o, l, g = res[i]
+        assert torch.equal(o, o0) and torch.equal(l, l0) and torch.equal(g[1], g0[1]) and torch.equal(g[2], g0[2])

@@ -85,13 +85,15 @@ REF_SEQ = [(1, 1), (1, 63), (1, 64), (1, 65), (1, 127), (1, 128), (1, 129), (1, 
            (511, 513), (513, 511), (383, 385), (385, 383), (2, 3)]
 
 
+@pytest.mark.parametrize("dtype", ["fp16", "bf16"])
 @pytest.mark.parametrize("d", [64, 128])
 @pytest.mark.parametrize("causal", [False, True])
 @pytest.mark.parametrize("nheads,nheads_k", [(2, 1), (6, 3), (4, 4)])
-def test_reference_shape_grid_fp16(d, causal, nheads, nheads_k):
-    """the reference's dense acceptance grid (fp16, GQA/MQA, ragged lengths) against the fp32 formulation its own
-    tests use; batch 3 for the small shapes, 1 for the 1k ones"""
-    dt = torch.float16
+def test_reference_shape_grid(d, causal, nheads, nheads_k, dtype):
+    """the reference's dense acceptance grid (GQA/MQA, ragged lengths) against the fp32 formulation its own tests use,
+    in fp16 (the reference's dtype) and bf16 (the dtype of every BASELINE config); batch 3 for the small shapes, 1 for
+    the 1k ones"""
+    dt = DT[dtype]
     for i, (sq, sk) in enumerate(REF_SEQ):
         b = 3 if max(sq, sk) <= 257 else 1
         torch.manual_seed(1000 * i + d)
