@@ -33,4 +33,6 @@ g++ -shared -o "$OUT/flash_attn_turing_ref.so" $OBJ/*.o -L"$TORCH_LIB" -lc10 -lt
     -L/usr/local/cuda/lib64 -lcudart -Wl,-rpath,"$TORCH_LIB"
 # the reference's own test file is needed on the GPU box to run its acceptance matrix unmodified
 cp "$REF/test_flash_attn.py" "$OUT/test_flash_attn.py"
+# ... and its benchmark harness (ncu command line + kernel-name classifier) for scripts/reference_harness.sh
+cp "$REF/benchmark.sh" "$OUT/benchmark.sh"; cp "$REF/utils/plot_kernels.py" "$OUT/plot_kernels.py"
 echo "built $OUT/flash_attn_turing_ref.so"

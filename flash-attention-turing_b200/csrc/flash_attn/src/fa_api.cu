@@ -127,7 +127,7 @@ static int validate_fwd(const fa_fwd_params* p) {
 
 #ifdef FA_TRACE
 static long long* g_trace = nullptr;
-constexpr size_t kTraceWords = 6 * 64 * 8;
+constexpr size_t kTraceWords = 8 * 64 * 8;
 long long* fa_trace_buffer(cudaStream_t stream) {
     if (!g_trace && cudaMalloc(&g_trace, kTraceWords * sizeof(long long)) != cudaSuccess) return nullptr;
     cudaMemsetAsync(g_trace, 0, kTraceWords * sizeof(long long), stream);

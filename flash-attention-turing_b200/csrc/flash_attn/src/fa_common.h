@@ -53,7 +53,7 @@ inline int ensure_dynamic_smem(Kern kern, int bytes, std::atomic<unsigned long l
 }
 
 #ifdef FA_TRACE
-// clock64 builds only (make trace): zeroed device buffer [6 roles][64 steps][8 events] the kernels of the next launch
+// clock64 builds only (make trace): zeroed device buffer [8 roles][64 steps][8 events] the kernels of the next launch
 // stamp; read back through fa_b200_trace_read (fa_api.cu)
 long long* fa_trace_buffer(cudaStream_t stream);
 #endif

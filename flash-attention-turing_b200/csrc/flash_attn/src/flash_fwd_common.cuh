@@ -18,13 +18,13 @@ struct FwdParams {
     float scale;       // 1/sqrt(d)
     float scale_log2;  // log2(e)/sqrt(d)
     float inv_scale_log2;
-    long long* trace;  // FA_TRACE builds only: clock64() stamps of CTA 0, [6 roles][64 steps][8 events]
+    long long* trace;  // FA_TRACE builds only: clock64() stamps of CTA 0, [8 roles][64 steps][8 events]
 };
 
 #ifdef FA_TRACE
 #define FA_TRACE_EVENT(role, j, ev)                                                              \
     do {                                                                                         \
-        if (p.trace && blockIdx.x == 0 && (role) < 6 && (j) < 64)                                 \
+        if (p.trace && blockIdx.x == 0 && (role) < 8 && (j) < 64)                                 \
             p.trace[((role) * 64 + (j)) * 8 + (ev)] = clock64();                                 \
     } while (0)
 #else
@@ -39,11 +39,34 @@ constexpr float kRescaleThreshold = 8.0f;
 
 
 // ---- persistent-kernel work list ----------------------------------------------------------------------
+// division by a runtime constant as multiply-high + shift (valid for numerators < 2^31): the work list is decoded by
+// every role at every item, and three 32-bit divisions cost ~250 cycles of dependent integer code each time
+struct FastDiv {
+    uint32_t d, mul, shr;
+};
+inline FastDiv make_fastdiv(uint32_t d) {
+    FastDiv f;
+    f.d = d; f.mul = 0; f.shr = 0;
+    if (d > 1) {
+        uint32_t lg = 0;
+        while ((1ull << lg) < d) ++lg;                       // ceil(log2 d)
+        const uint32_t pw = 31 + lg;
+        f.mul = (uint32_t)(((1ull << pw) + d - 1) / d);
+        f.shr = pw - 32;
+    }
+    return f;
+}
+FA_DEVICE int fast_div(int n, const FastDiv& f) { return f.d == 1 ? n : (int)(__umulhi((uint32_t)n, f.mul) >> f.shr); }
+
 struct TileSched {
     int num_mblk;      // 256-row query blocks per (batch, head)
     int bh;            // batch * heads
     int group;         // (batch, head) pairs per L2 group
     int total;         // num_mblk * bh
+    FastDiv per_group; // group * num_mblk
+    FastDiv full;      // heads in a full group (= group)
+    FastDiv last;      // heads in the last, possibly smaller group
+    FastDiv heads;     // h
 };
 
 struct WorkItem {
@@ -51,16 +74,16 @@ struct WorkItem {
 };
 
 FA_DEVICE WorkItem decode_item(const TileSched& ts, int n, int h, bool causal) {
-    const int per_group = ts.group * ts.num_mblk;
-    const int g = n / per_group;
-    int r = n - g * per_group;
-    const int heads_here = min(ts.group, ts.bh - g * ts.group);   // the last group may be smaller
-    const int level = r / heads_here;
+    const int g = fast_div(n, ts.per_group);
+    const int r = n - g * (int)ts.per_group.d;
+    const bool is_last = (g + 1) * ts.group > ts.bh;              // the last group may be smaller
+    const int heads_here = is_last ? (int)ts.last.d : ts.group;
+    const int level = is_last ? fast_div(r, ts.last) : fast_div(r, ts.full);
     const int head_local = r - level * heads_here;
     const int bhi = g * ts.group + head_local;
     WorkItem w;
     w.mblk = causal ? (ts.num_mblk - 1 - level) : level;          // heaviest causal row blocks first
-    w.bidb = bhi / h;
+    w.bidb = fast_div(bhi, ts.heads);
     w.bidh = bhi - w.bidb * h;
     return w;
 }
@@ -118,6 +141,11 @@ inline TileSched make_tile_sched(const fa_fwd_params* p) {
     if (grp > ts.bh) grp = ts.bh;
     ts.group = (int)grp;
     ts.total = ts.num_mblk * ts.bh;
+    ts.per_group = make_fastdiv((uint32_t)(ts.group * ts.num_mblk));
+    ts.full = make_fastdiv((uint32_t)ts.group);
+    const int last_heads = ts.bh - (ts.bh - 1) / ts.group * ts.group;   // 1 .. group
+    ts.last = make_fastdiv((uint32_t)last_heads);
+    ts.heads = make_fastdiv((uint32_t)p->h);
     return ts;
 }
 

@@ -31,6 +31,9 @@
 
 #include "flash_fwd_common.cuh"
 
+#ifndef FA_P4_EXPERIMENT_NOMAX
+#define FA_P4_EXPERIMENT_NOMAX 0
+#endif
 #ifndef FA_P4_PASS1_WIDE
 #define FA_P4_PASS1_WIDE 0   // 1: pass 1 loads all four score chunks at once (64 registers in flight) instead of 32 + 16 + 16
 #endif
@@ -154,6 +157,10 @@ flash_fwd_kernel_sm100_p4(const __grid_constant__ CUtensorMap tmQ, const __grid_
             }
         } else if (warp == 16) {
             // ===================== MMA issuer (warp-uniform walk, one elected lane issues) =====================
+            // ONE warp issues for both tiles, strictly alternating (tile 0: four P quarters + next S) (tile 1: ...).  That
+            // alternation is what keeps the two tiles half a period apart — one in its softmax while the other's MMAs run.
+            // Measured (profiles/r02_run5.log): one issuing warp per tile lets the tiles drift into the SAME phase (both
+            // softmax, then both MMA) and the period grows from ~2850 to ~3760 cycles (C2 1106 instead of 1322 TFLOP/s).
             const bool leader = elect_one();
             constexpr uint32_t idesc_s = make_idesc(kBf16, kBlockM, kBlockN, false, false);
             constexpr uint32_t idesc_pv = make_idesc(kBf16, kBlockM, D, false, true);
@@ -242,6 +249,35 @@ flash_fwd_kernel_sm100_p4(const __grid_constant__ CUtensorMap tmQ, const __grid_
                 it[0] += nb0; it[1] += nb1;
                 nitem[0] += (nb0 > 0); nitem[1] += (nb1 > 0);
             }
+        } else {
+            // ===================== warps 18 / 19: TMA store of tile slot 0 / 1 =====================
+            // The softmax warpgroups only write the staging tile and arrive on a named barrier; issuing the bulk store and
+            // waiting for the engine to read 32 KB of shared memory (~1800 cycles) is this warp's job.  When a softmax
+            // thread did it, its whole warp sat in that wait and — every P quarter needs all eight warps of a tile — held
+            // up the tile's first key steps of the next item (clock64: the next item's first S was picked up ~1200 cycles
+            // after the epilogue had finished, profiles/r02_run3.log).
+            const int t = warp - 18;
+            for (int n = blockIdx.x; n < ts.total; n += gridDim.x) {
+                const WorkItem w = decode_item(ts, n, p.h, p.is_causal != 0);
+                const ItemGeom g = item_geom(p, w);
+                if (g.skip) continue;
+                const int mt = g.m0 + t * kBlockM;
+                if (mt >= g.sq_b || g.nblk[t] == 0) continue;
+                const bool whole_tile = (mt + kBlockM <= g.sq_b) || (p.cu_q == nullptr);
+                if (!whole_tile) continue;                         // ragged varlen tail: stored by the softmax threads themselves
+                named_bar_sync(11 + t, 2 * kBlockM + 32);          // staging tile written and fenced by the tile's 256 threads
+                if (lane == 0) {
+#pragma unroll
+                    for (int sl = 0; sl < kSlabs; ++sl)
+                        tma_store_4d(&tmO, sStage + sl * L::kSlab, sl * 64, w.bidh, g.q_row0 + mt, g.tma_b);
+                    tma_store_commit();
+                    tma_store_wait_read<0>();                      // staging tile has been read; global writes complete later
+                    __threadfence_block();
+                    atomicExch(stage_lock, 0);                     // the other tile's epilogue (or this tile's next one) may take it
+                }
+                __syncwarp();
+            }
+            if (lane == 0) tma_store_wait<0>();                    // all bulk stores have landed before the CTA retires
         }
     } else {
         // ========== softmax warpgroups: warpgroup 2t+hh owns columns [64hh, 64hh+64) of tile slot t, one thread per row ==========
@@ -317,7 +353,8 @@ flash_fwd_kernel_sm100_p4(const __grid_constant__ CUtensorMap tmQ, const __grid_
         // (column half 1, quadrant 3); events 0 S full, 1 max exchanged, 2..5 quarter q handed over, 6 O full, 7 epilogue done
         const int trole = (hh == 0 && wq == 0) ? t : (hh == 1 && wq == 3) ? 2 + t : 99;
         int tr_step = 0;
-        (void)trole; (void)tr_step;
+        const int erole = (hh == 0 && wq == 0) ? 6 + t : 99;   // rows 6 / 7: epilogue stamps of warp 0 of tile 0 / 1, one row per item
+        (void)trole; (void)tr_step; (void)erole;
         // A quarter of P leaves in two steps: the TMEM store is issued as soon as the chunk's exponentials are done, the
         // hand-over to the MMA warp (wait::st, fence, one elected arrive per warp) half a chunk later, underneath the next
         // chunk's exponentials.  Waiting for the store right behind its issue cost ~130 cycles per quarter with both warps
@@ -365,10 +402,11 @@ flash_fwd_kernel_sm100_p4(const __grid_constant__ CUtensorMap tmQ, const __grid_
             }
             float m_ref = -INFINITY, l_run = 0.f;
 
-            for (int j = 0; j < n_t; ++j) {
-                const bool need_mask = j >= j_mask;
+            auto key_step = [&](auto mask_tag, const int j) {
+                constexpr bool need_mask = decltype(mask_tag)::value;   // masked and unmasked steps get separate straight-line copies
                 tr_step = its + j;
                 const int lim = lim0 - j * kBlockN;            // last visible column of this thread's 64 (may be < 0 or >= 64)
+                if (j == 0 && (tid & 31) == 0) FA_TRACE_EVENT(trole, its, 7);   // first step of an item: about to wait for its S
                 mbar_wait(&bar_s_full[t], (its + j) & 1);
                 tc_fence_after();
                 if ((tid & 31) == 0) FA_TRACE_EVENT(trole, its + j, 0);
@@ -376,6 +414,14 @@ flash_fwd_kernel_sm100_p4(const __grid_constant__ CUtensorMap tmQ, const __grid_
                 // ---- pass 1: exact row max of the 64 own scores; chunk 0 stays in registers for pass 2 ----
                 float sa[16];
                 float mx;
+#if FA_P4_EXPERIMENT_NOMAX   // TIMING EXPERIMENT ONLY (wrong for data whose row max grows after the first key tile)
+                if (j > 0) {
+                    tmem_ld16(tS, *reinterpret_cast<uint32_t(*)[16]>(&sa[0]));
+                    tmem_wait_ld();
+                    if constexpr (need_mask) mask_chunk(sa, lim);
+                    mx = m_ref;
+                } else
+#endif
                 {
 #if FA_P4_PASS1_WIDE
                     float sc[16], sd[16], sb[16];
@@ -384,7 +430,7 @@ flash_fwd_kernel_sm100_p4(const __grid_constant__ CUtensorMap tmQ, const __grid_
                     tmem_ld16(tS + 16, *reinterpret_cast<uint32_t(*)[16]>(&sb[0]));
                     tmem_ld16(tS, *reinterpret_cast<uint32_t(*)[16]>(&sa[0]));
                     tmem_wait_ld();
-                    if (need_mask) { mask_chunk(sc, lim - 32); mask_chunk(sd, lim - 48); mask_chunk(sb, lim - 16); mask_chunk(sa, lim); }
+                    if constexpr (need_mask) { mask_chunk(sc, lim - 32); mask_chunk(sd, lim - 48); mask_chunk(sb, lim - 16); mask_chunk(sa, lim); }
                     mx = fmaxf(fmaxf(max_chunk(sc), max_chunk(sd)), fmaxf(max_chunk(sb), max_chunk(sa)));
 #else
                     float sc[16], sd[16], sb[16];
@@ -392,22 +438,27 @@ flash_fwd_kernel_sm100_p4(const __grid_constant__ CUtensorMap tmQ, const __grid_
                     tmem_ld16(tS + 48, *reinterpret_cast<uint32_t(*)[16]>(&sd[0]));
                     tmem_wait_ld();
                     tmem_ld16(tS + 16, *reinterpret_cast<uint32_t(*)[16]>(&sb[0]));
-                    if (need_mask) { mask_chunk(sc, lim - 32); mask_chunk(sd, lim - 48); }
+                    if constexpr (need_mask) { mask_chunk(sc, lim - 32); mask_chunk(sd, lim - 48); }
                     mx = fmaxf(max_chunk(sc), max_chunk(sd));
                     tmem_wait_ld();
                     tmem_ld16(tS, *reinterpret_cast<uint32_t(*)[16]>(&sa[0]));
-                    if (need_mask) mask_chunk(sb, lim - 16);
+                    if constexpr (need_mask) mask_chunk(sb, lim - 16);
                     mx = fmaxf(mx, max_chunk(sb));
                     tmem_wait_ld();
-                    if (need_mask) mask_chunk(sa, lim);
+                    if constexpr (need_mask) mask_chunk(sa, lim);
                     mx = fmaxf(mx, max_chunk(sa));
 #endif
                 }
-                sts32f(x_own, mx);
-                named_bar_sync(pair_bar, 64);
-                float mp;
-                asm volatile("ld.shared.f32 %0, [%1];" : "=f"(mp) : "r"(x_own ^ (kBlockM * 4)));
-                mx = fmaxf(mx, mp);
+#if FA_P4_EXPERIMENT_NOMAX
+                if (j == 0)
+#endif
+                {
+                    sts32f(x_own, mx);
+                    named_bar_sync(pair_bar, 64);
+                    float mp;
+                    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(mp) : "r"(x_own ^ (kBlockM * 4)));
+                    mx = fmaxf(mx, mp);
+                }
                 if ((tid & 31) == 0) FA_TRACE_EVENT(trole, its + j, 1);
                 // lazy reference: it moves only when the row max grew by more than 2^8 (always on the first visible key)
                 const bool need = (mx - m_ref) * c2 > kRescaleThreshold;
@@ -450,20 +501,20 @@ flash_fwd_kernel_sm100_p4(const __grid_constant__ CUtensorMap tmQ, const __grid_
                     tmem_st8(tS, pka);
                     tmem_wait_ld();
                     tmem_ld16(tS + 32, *reinterpret_cast<uint32_t(*)[16]>(&sa[0]));
-                    if (need_mask) mask_chunk(sb, lim - 16);
+                    if constexpr (need_mask) mask_chunk(sb, lim - 16);
                     exp_half(h0{}, sb, neg, pkb, sum);
                     arrive_quarter(0);
                     exp_half(h1{}, sb, neg, pkb, sum);
                     tmem_st8(tS + 8, pkb);
                     tmem_wait_ld();
                     tmem_ld16(tS + 48, *reinterpret_cast<uint32_t(*)[16]>(&sb[0]));
-                    if (need_mask) mask_chunk(sa, lim - 32);
+                    if constexpr (need_mask) mask_chunk(sa, lim - 32);
                     exp_half(h0{}, sa, neg, pka, sum);
                     arrive_quarter(1);
                     exp_half(h1{}, sa, neg, pka, sum);
                     tmem_st8(tS + 16, pka);
                     tmem_wait_ld();
-                    if (need_mask) mask_chunk(sb, lim - 48);
+                    if constexpr (need_mask) mask_chunk(sb, lim - 48);
                     exp_half(h0{}, sb, neg, pkb, sum);
                     arrive_quarter(2);
                     exp_half(h1{}, sb, neg, pkb, sum);
@@ -471,13 +522,18 @@ flash_fwd_kernel_sm100_p4(const __grid_constant__ CUtensorMap tmQ, const __grid_
                     arrive_quarter(3);
                 }
                 l_run += sum.x + sum.y;
+            };
+            for (int j = 0; j < n_t; ++j) {
+                if (j >= j_mask) key_step(std::true_type{}, j);
+                else key_step(std::false_type{}, j);
             }
             its += n_t;
 
             // ---- epilogue: O_t / l -> 16 bit -> staging tile (128B-swizzled, the TMA layout) -> TMA store ----
-            mbar_wait(&bar_o_full[t], nitem & 1);
+            if ((tid & 31) == 0) FA_TRACE_EVENT(erole, nitem, 0);     // rows 6 / 7: epilogue of item `nitem` (0 start, 1 O full, 2 l exchanged,
+            mbar_wait(&bar_o_full[t], nitem & 1);                  //   3 staging tile taken, 4 O in registers, 5 staged, 6 handed over)
             tc_fence_after();
-            if ((tid & 31) == 0) FA_TRACE_EVENT(trole, its - 1, 6);
+            if ((tid & 31) == 0) FA_TRACE_EVENT(erole, nitem, 1);
             int n_again = n;
             asm volatile("" : "+r"(n_again));                  // opaque copy: keeps the geometry from living across the key loop
             const WorkItem w = decode_item(ts, n_again, p.h, p.is_causal != 0);
@@ -493,6 +549,7 @@ flash_fwd_kernel_sm100_p4(const __grid_constant__ CUtensorMap tmQ, const __grid_
             const float l_tot = l_run + l_peer;
             const bool row_empty = (m_ref == -INFINITY) || !(l_tot > 0.f);   // no visible key: O = 0, LSE = 0
             const float inv_l = row_empty ? 0.f : (1.f / l_tot);
+            if ((tid & 31) == 0) FA_TRACE_EVENT(erole, nitem, 2);
             if (hh == 0 && wq == 0) {    // take the staging tile (the other tile's epilogue may hold it); the whole warp spins
                 int got;                 // together: bar.sync below is warp-aligned
                 do {
@@ -503,6 +560,7 @@ flash_fwd_kernel_sm100_p4(const __grid_constant__ CUtensorMap tmQ, const __grid_
                 } while (!got);
             }
             named_bar_sync(tile_bar, 2 * kBlockM);
+            if ((tid & 31) == 0) FA_TRACE_EVENT(erole, nitem, 3);
             const uint32_t stage = smem_u32(sStage);
 #pragma unroll
             for (int c = 0; c < kHalfD / 32; ++c) {
@@ -513,6 +571,7 @@ flash_fwd_kernel_sm100_p4(const __grid_constant__ CUtensorMap tmQ, const __grid_
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&bar_o_empty[t]);
+                    if (lane == 0) FA_TRACE_EVENT(erole, nitem, 4);
                 }
 #pragma unroll
                 for (int q4 = 0; q4 < 4; ++q4) {
@@ -526,23 +585,15 @@ flash_fwd_kernel_sm100_p4(const __grid_constant__ CUtensorMap tmQ, const __grid_
                 }
             }
             if (hh == 0 && row < g.sq_b) lse_row[row] = row_empty ? 0.f : (m_ref * p.scale + logf(l_tot));
+            if ((tid & 31) == 0) FA_TRACE_EVENT(erole, nitem, 5);
             fence_proxy_async_smem();                          // generic-proxy writes -> visible to the TMA engine
             const bool whole_tile = (mt + kBlockM <= g.sq_b) || (p.cu_q == nullptr);   // dense: TMA clips rows >= seqlen_q itself
-            named_bar_sync(tile_bar, 2 * kBlockM);
             if (whole_tile) {
-                if (hh == 0 && r_in_tile == 0) {
-#pragma unroll
-                    for (int sl = 0; sl < kSlabs; ++sl)
-                        tma_store_4d(&tmO, sStage + sl * L::kSlab, sl * 64, w.bidh, g.q_row0 + mt, g.tma_b);
-                    tma_store_commit();
-                    tma_store_wait_read<0>();                  // staging tile has been read; global writes complete later
-                    __threadfence_block();
-                    atomicExch(stage_lock, 0);
-                }
-                __syncwarp();
+                named_bar_arrive(11 + t, 2 * kBlockM + 32);    // hand the staging tile to store warp 18 + t (it releases the lock) and move on
             } else {
                 // ragged varlen tail: a TMA box would spill into the next sequence -> predicated coalesced stores
                 constexpr int kChunksPerRow = D / 8;
+                named_bar_sync(tile_bar, 2 * kBlockM);
                 for (int idx = hh * kBlockM + r_in_tile; idx < kBlockM * kChunksPerRow; idx += 2 * kBlockM) {
                     const int rr = idx / kChunksPerRow, ch = idx % kChunksPerRow;
                     if (mt + rr < g.sq_b) {
@@ -554,10 +605,10 @@ flash_fwd_kernel_sm100_p4(const __grid_constant__ CUtensorMap tmQ, const __grid_
                 if (hh == 0 && r_in_tile == 0) atomicExch(stage_lock, 0);
                 __syncwarp();
             }
-            if ((tid & 31) == 0) FA_TRACE_EVENT(trole, its - 1, 7);
+            if ((tid & 31) == 0) FA_TRACE_EVENT(trole, its - 1, 6);
+            if ((tid & 31) == 0) FA_TRACE_EVENT(erole, nitem, 6);
             ++nitem;
         }
-        if (hh == 0 && r_in_tile == 0) tma_store_wait<0>();   // all bulk stores of this thread have landed before the CTA retires
     }
 
     tc_fence_before();

@@ -64,6 +64,28 @@ def test_host_pipeline_chunk_ranges():
             assert sum(e - s for s, e in r) == b and all(e > s for s, e in r)
 
 
+def test_host_pipeline_chunk_plan():
+    """batch ranges first; beyond `batch` chunks the KV heads of every batch are split into equal groups"""
+    from flash_attn_turing.hostio import plan_chunks
+    assert plan_chunks(4, 32, 4) == [(0, 1, 0, 32), (1, 2, 0, 32), (2, 3, 0, 32), (3, 4, 0, 32)]
+    assert plan_chunks(4, 32, None) == [(b, b + 1, 8 * g, 8 * g + 8) for b in range(4) for g in range(4)]
+    assert plan_chunks(5, 2, None) == [(b, b + 1, g, g + 1) for b in range(5) for g in range(2)]
+    assert plan_chunks(5, 2, 2) == [(0, 3, 0, 2), (3, 5, 0, 2)]
+    assert plan_chunks(2, 6, 9) == [(b, b + 1, 2 * g, 2 * g + 2) for b in range(2) for g in range(3)]   # 4 per batch -> 3 divides 6
+    assert plan_chunks(3, 1, 16) == [(0, 1, 0, 1), (1, 2, 0, 1), (2, 3, 0, 1)]
+    assert plan_chunks(0, 4, None) == []
+    for b in range(1, 7):
+        for hk in (1, 2, 3, 8):
+            for n in (None, 1, 2, 5, 16, 64):
+                cover = set()
+                for b0, b1, g0, g1 in plan_chunks(b, hk, n):
+                    for bi in range(b0, b1):
+                        for g in range(g0, g1):
+                            assert (bi, g) not in cover
+                            cover.add((bi, g))
+                assert len(cover) == b * hk
+
+
 def test_shard_ranges():
     sh = _load_sharded()
     assert sh.shard_ranges(256, 8) == [(32 * i, 32 * i + 32) for i in range(8)]

@@ -155,3 +155,31 @@ def test_dq_kernel_key_ranges_and_mask_agree_with_the_elementwise_rule():
                         assert kernel_visible == truth_visible, (sq, sk, causal, m0, row, j, c)
                 # nothing visible beyond the visited tiles
                 assert all(not (k < sk and ((not causal) or k <= row + off)) for k in range(nb * 128, min(sk, nb * 128 + 256)))
+
+
+def _make_fastdiv(d):
+    """restatement of make_fastdiv (flash_fwd_common.cuh): divisor -> (mul, shr) with n // d == (n * mul >> 32) >> shr"""
+    if d == 1:
+        return 0, 0
+    lg = 0
+    while (1 << lg) < d:
+        lg += 1
+    pw = 31 + lg
+    return ((1 << pw) + d - 1) // d, pw - 32
+
+
+def test_fastdiv_matches_integer_division_below_2_31():
+    """the work-list decode divides by (group * num_mblk), the group size and the head count with multiply-high + shift"""
+    import random
+    rnd = random.Random(0)
+    divisors = list(range(1, 300)) + [2 ** k for k in range(1, 31)] + [2 ** k - 1 for k in range(2, 31)] + [2 ** k + 1 for k in range(1, 30)] \
+        + [rnd.randrange(1, 2 ** 31) for _ in range(300)]
+    for d in divisors:
+        mul, shr = _make_fastdiv(d)
+        assert mul < 2 ** 32, d
+        ns = [0, 1, d - 1, d, d + 1, 2 * d - 1, 2 * d, 2 ** 31 - 1, 2 ** 31 - d, (2 ** 31 - 1) // d * d, (2 ** 31 - 1) // d * d - 1] \
+            + [rnd.randrange(0, 2 ** 31) for _ in range(200)]
+        for n in ns:
+            if 0 <= n < 2 ** 31:
+                q = n if d == 1 else ((n * mul) >> 32) >> shr
+                assert q == n // d, (n, d, q, n // d)
