@@ -15,6 +15,7 @@ struct FwdParams {
     const int* cu_k;
     int b, sq, sk, h, h_k, hratio;
     int is_causal;
+    int exact;         // 1: every key step computes the exact row max first (no speculative steps); FA_B200_FWD_EXACT
     float scale;       // 1/sqrt(d)
     float scale_log2;  // log2(e)/sqrt(d)
     float inv_scale_log2;

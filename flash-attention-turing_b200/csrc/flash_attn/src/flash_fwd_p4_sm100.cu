@@ -42,11 +42,16 @@ namespace fa100 {
 
 namespace {
 constexpr int kThreadsP4 = 640;
+constexpr int kMaxRetry = 48;
 template <int D> struct P4Smem {
     static constexpr int kSlab = kBlockM * 128;          // 64-column slab of a 128-row tile: 16 KB
     static constexpr int kSlabs = D / 64;
     static constexpr int kTile = kSlabs * kSlab;         // one 128 x D tile (32 KB / 16 KB)
-    static constexpr int kStages = (D == 128) ? 4 : 8;   // K/V ring: K_j -> slot 2j, V_j -> slot 2j+1 (128 KB)
+    // K/V ring of four tiles (D = 128): V_j, K_j+1 in use, V_j+1 and K_j+2 arriving.  Three slots are not enough: K_j+2 could
+    // then only be requested when V_j is released (end of step j) and is needed half a period later — clock64 showed the
+    // MMA warp waiting 500-600 cycles per step for K and V, C2 dropped from ~1300 to ~1200 TFLOP/s (profiles/r02_run8.log).
+    // So there is ONE O staging tile for both query tiles, guarded by a lock.
+    static constexpr int kStages = (D == 128) ? 4 : 8;
     static constexpr int kOffQ = 0;                      // 2 tiles
     static constexpr int kOffKV = 2 * kTile;
     static constexpr int kOffStage = kOffKV + kStages * kTile;   // 16-bit O tile: source of the TMA store
@@ -90,11 +95,16 @@ flash_fwd_kernel_sm100_p4(const __grid_constant__ CUtensorMap tmQ, const __grid_
     uint64_t* bar_o_empty = bar_o_full + 2;           // [2]  epilogue has O_t in registers (8 arrivals)
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_o_empty + 2);
     int* stage_lock = reinterpret_cast<int*>(tmem_slot + 1);   // the two tiles' epilogues share one staging tile
+    int* retry_count = stage_lock + 1;                // items whose speculative pass overflowed (see "late-agreed reference")
+    int* poison = stage_lock + 2;                     // [2 tiles][2 item parities]: some row of the tile overflowed in this item
+    int* retry_list = stage_lock + 6;                 // [kMaxRetry] work-item indices, deduplicated at the pass boundary
     const uint32_t xch = smem_u32(smem + L::kOffXch);
 
     if (warp == 16) {
         if (lane == 0) {
             *stage_lock = 0;
+            *retry_count = 0;
+            poison[0] = poison[1] = poison[2] = poison[3] = 0;
             for (int t = 0; t < 2; ++t) {
                 mbar_init(&bar_q_full[t], 1); mbar_init(&bar_q_empty[t], 1);
                 mbar_init(&bar_s_full[t], 1);
@@ -115,14 +125,49 @@ flash_fwd_kernel_sm100_p4(const __grid_constant__ CUtensorMap tmQ, const __grid_
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
+    // ---- work list: pass 0 = this CTA's share of the static schedule; pass 1 = the items of pass 0 in which some row's
+    // speculative exponentials overflowed (retry list in shared memory), redone with the exact per-step row max ----
+    const int n_static = (ts.total > (int)blockIdx.x) ? (ts.total - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+    auto pass_count = [&](int pass) -> int {
+        if (pass == 0) return n_static;
+        const int c = *reinterpret_cast<volatile int*>(retry_count);
+        return c > kMaxRetry ? n_static : c;          // list overflow: redo everything
+    };
+    auto pass_item = [&](int pass, int idx) -> int {
+        if (pass == 0 || *reinterpret_cast<volatile int*>(retry_count) > kMaxRetry) return (int)blockIdx.x + idx * (int)gridDim.x;
+        return reinterpret_cast<volatile int*>(retry_list)[idx];
+    };
+    // every thread of the CTA calls this once, between the passes (each role from its own branch: barrier 0 counts threads)
+    auto pass_boundary = [&]() {
+        __syncthreads();
+        if (tid == 0) {
+            const int c = *retry_count;
+            if (c <= kMaxRetry) {                     // both tiles of an item may have queued it: keep one copy
+                int m = 0;
+                for (int i = 0; i < c; ++i) {
+                    const int v = retry_list[i];
+                    bool dup = false;
+                    for (int k2 = 0; k2 < m; ++k2) dup = dup || (retry_list[k2] == v);
+                    if (!dup) retry_list[m++] = v;
+                }
+                *retry_count = m;
+            }
+        }
+        __syncthreads();
+    };
+    const bool exact0 = p.exact != 0;                 // FA_B200_FWD_EXACT=1: no speculation at all (A/B runs, debugging)
+
     if (wg == 4) {
         setmaxnreg_dec<64>();
         if (warp == 17) {
             // ===================== TMA producer =====================
-            if (lane == 0) {
-                int kv_i = 0;            // running K/V ring index
-                int nq[2] = {0, 0};      // Q_t loads so far
-                for (int n = blockIdx.x; n < ts.total; n += gridDim.x) {
+            int kv_i = 0;            // running K/V ring index
+            int nq[2] = {0, 0};      // Q_t loads so far
+            for (int pass = 0; pass < 2; ++pass) {
+              const int cnt = pass_count(pass);
+              if (lane == 0) {
+                for (int idx = 0; idx < cnt; ++idx) {
+                    const int n = pass_item(pass, idx);
                     const WorkItem w = decode_item(ts, n, p.h, p.is_causal != 0);
                     const ItemGeom g = item_geom(p, w);
                     if (g.skip || g.n_blocks == 0) continue;
@@ -154,6 +199,9 @@ flash_fwd_kernel_sm100_p4(const __grid_constant__ CUtensorMap tmQ, const __grid_
                         load_kv(&tmV, j);
                     }
                 }
+              }
+              __syncwarp();
+              if (pass == 0) { pass_boundary(); if (pass_count(1) == 0) break; }
             }
         } else if (warp == 16) {
             // ===================== MMA issuer (warp-uniform walk, one elected lane issues) =====================
@@ -172,7 +220,10 @@ flash_fwd_kernel_sm100_p4(const __grid_constant__ CUtensorMap tmQ, const __grid_
             int kv_i = 0;                 // ring index of K_0 of the current item
             int it[2] = {0, 0};           // S_t / P_t steps so far (barrier parities)
             int nitem[2] = {0, 0};        // items finished per tile slot (Q / O barrier parities)
-            for (int n = blockIdx.x; n < ts.total; n += gridDim.x) {
+            for (int pass = 0; pass < 2; ++pass) {
+              const int cnt = pass_count(pass);
+              for (int idx = 0; idx < cnt; ++idx) {
+                const int n = pass_item(pass, idx);
                 const WorkItem w = decode_item(ts, n, p.h, p.is_causal != 0);
                 const ItemGeom g = item_geom(p, w);
                 const int nb0 = __shfl_sync(0xffffffffu, g.nblk[0], 0);
@@ -213,8 +264,10 @@ flash_fwd_kernel_sm100_p4(const __grid_constant__ CUtensorMap tmQ, const __grid_
                 if (nb0 > 0) { mbar_wait(&bar_q_full[0], nitem[0] & 1); issue_s(0, 0, nb0); }
                 if (nb1 > 0) { mbar_wait(&bar_q_full[1], nitem[1] & 1); issue_s(1, 0, nb1); }
                 commit(&bar_kv_empty[kv_slot(0)]);
+                bool v_ready = false;     // V_j was already seen full by the probe of the previous step
                 for (int j = 0; j < nbmax; ++j) {
-                    wait_kv(2 * j + 1);  // V_j
+                    if (!v_ready) wait_kv(2 * j + 1);  // V_j
+                    v_ready = false;
                     bool k_ready = false;
 #pragma unroll
                     for (int t = 0; t < 2; ++t) {
@@ -223,17 +276,31 @@ flash_fwd_kernel_sm100_p4(const __grid_constant__ CUtensorMap tmQ, const __grid_
                             if (j == 0) {   // O_t of the previous item must have been read out by its epilogue
                                 mbar_wait(&bar_o_empty[t], (nitem[t] & 1) ^ 1);
                             }
-#pragma unroll
-                            for (int q = 0; q < 4; ++q) {
-                                mbar_wait(&bar_p[4 * t + q], (it[t] + j) & 1);
+                            // The softmax warps hand P over quarter by quarter, in order.  When this warp gets here late (the
+                            // usual case: it was issuing the other tile's MMAs) all four quarters are there already, and four
+                            // waits on completed barriers (~90-200 cycles each with the sub-partition's softmax warps competing
+                            // for issue slots) let the tensor pipe run dry: probe the LAST quarter first.
+                            if (mbar_test_wait(&bar_p[4 * t + 3], (it[t] + j) & 1)) {
                                 tc_fence_after();
-                                if (lane == 0) FA_TRACE_EVENT(4 + t, it[t] + j, q);      // rows 4 / 5: MMA warp, tile 0 / 1
-                                issue_pv(t, j, q);
+                                if (lane == 0) FA_TRACE_EVENT(4 + t, it[t] + j, 3);
+#pragma unroll
+                                for (int q = 0; q < 4; ++q) issue_pv(t, j, q);
+                            } else {
+#pragma unroll
+                                for (int q = 0; q < 4; ++q) {
+                                    mbar_wait(&bar_p[4 * t + q], (it[t] + j) & 1);
+                                    tc_fence_after();
+                                    if (lane == 0) FA_TRACE_EVENT(4 + t, it[t] + j, q);      // rows 4 / 5: MMA warp, tile 0 / 1
+                                    issue_pv(t, j, q);
+                                }
                             }
                             if (lane == 0) FA_TRACE_EVENT(4 + t, it[t] + j, 4);
                             if (j + 1 < nbt) {
                                 if (!k_ready) { wait_kv(2 * j + 2); tc_fence_after(); k_ready = true; }
                                 if (lane == 0) FA_TRACE_EVENT(4 + t, it[t] + j, 5);
+                                // probe V_j+1 now, underneath the eight MMAs about to be queued, instead of after them
+                                if (t == 1 && j + 1 < nbmax)
+                                    v_ready = mbar_test_wait(&bar_kv_full[kv_slot(2 * j + 3)], (((kv_i + 2 * j + 3) / kStages) & 1));
                                 issue_s(t, j + 1, nbt);
                             } else {
                                 commit(&bar_o_full[t]);
@@ -248,6 +315,8 @@ flash_fwd_kernel_sm100_p4(const __grid_constant__ CUtensorMap tmQ, const __grid_
                 kv_i += 2 * nbmax;
                 it[0] += nb0; it[1] += nb1;
                 nitem[0] += (nb0 > 0); nitem[1] += (nb1 > 0);
+              }
+              if (pass == 0) { pass_boundary(); if (pass_count(1) == 0) break; }
             }
         } else {
             // ===================== warps 18 / 19: TMA store of tile slot 0 / 1 =====================
@@ -257,16 +326,27 @@ flash_fwd_kernel_sm100_p4(const __grid_constant__ CUtensorMap tmQ, const __grid_
             // up the tile's first key steps of the next item (clock64: the next item's first S was picked up ~1200 cycles
             // after the epilogue had finished, profiles/r02_run3.log).
             const int t = warp - 18;
-            for (int n = blockIdx.x; n < ts.total; n += gridDim.x) {
+            int nit = 0;                                           // items in which this tile had keys (= the softmax warps' nitem)
+            for (int pass = 0; pass < 2; ++pass) {
+              const int cnt = pass_count(pass);
+              for (int idx = 0; idx < cnt; ++idx) {
+                const int n = pass_item(pass, idx);
                 const WorkItem w = decode_item(ts, n, p.h, p.is_causal != 0);
                 const ItemGeom g = item_geom(p, w);
                 if (g.skip) continue;
                 const int mt = g.m0 + t * kBlockM;
                 if (mt >= g.sq_b || g.nblk[t] == 0) continue;
+                const int par = nit & 1;
+                ++nit;
                 const bool whole_tile = (mt + kBlockM <= g.sq_b) || (p.cu_q == nullptr);
                 if (!whole_tile) continue;                         // ragged varlen tail: stored by the softmax threads themselves
                 named_bar_sync(11 + t, 2 * kBlockM + 32);          // staging tile written and fenced by the tile's 256 threads
                 if (lane == 0) {
+                    if (poison[2 * t + par]) {                     // some row of this tile overflowed its speculative step: redo the item
+                        poison[2 * t + par] = 0;
+                        const int k2 = atomicAdd(retry_count, 1);
+                        if (k2 < kMaxRetry) retry_list[k2] = n;
+                    }
 #pragma unroll
                     for (int sl = 0; sl < kSlabs; ++sl)
                         tma_store_4d(&tmO, sStage + sl * L::kSlab, sl * 64, w.bidh, g.q_row0 + mt, g.tma_b);
@@ -276,8 +356,11 @@ flash_fwd_kernel_sm100_p4(const __grid_constant__ CUtensorMap tmQ, const __grid_
                     atomicExch(stage_lock, 0);                     // the other tile's epilogue (or this tile's next one) may take it
                 }
                 __syncwarp();
+              }
+              if (lane == 0) tma_store_wait<0>();                  // all bulk stores have landed before a retry rewrites the tile / the CTA retires
+              __syncwarp();
+              if (pass == 0) { pass_boundary(); if (pass_count(1) == 0) break; }
             }
-            if (lane == 0) tma_store_wait<0>();                    // all bulk stores have landed before the CTA retires
         }
     } else {
         // ========== softmax warpgroups: warpgroup 2t+hh owns columns [64hh, 64hh+64) of tile slot t, one thread per row ==========
@@ -294,18 +377,20 @@ flash_fwd_kernel_sm100_p4(const __grid_constant__ CUtensorMap tmQ, const __grid_
         const uint32_t tO = tmem_base + lane_base + kTmemO0 + t * 128 + hh * kHalfD;   // own half of the O row
         const uint32_t x_own = xch + ((t * 2 + hh) * kBlockM + r_in_tile) * 4;
         const uint32_t pair_bar = 1 + t * 4 + wq;       // named barriers 1..8: the two warps that share 32 rows (64 threads)
-        const uint32_t tile_bar = 9 + t;                // named barriers 9, 10: the two warpgroups of a tile (256 threads)
+        const uint32_t tile_bar = 9 + t;                // named barriers 9, 10: the two warpgroups of a tile (256 threads); 11, 12: + its store warp
         uint16_t* o_base = reinterpret_cast<uint16_t*>(p.o);
         const float c2 = p.scale_log2;
         int its = 0;       // S_t steps so far
         int nitem = 0;     // items with keys finished by this slot
+        uint32_t hs16 = 0; // own sum of the previous key step, top 16 bits (what the peer thread reads one step late)
 
         // P = 2^(s*c2 + neg) for one 16-column chunk; kEmu selects how many of every 8 column pairs go through the
         // Cody-Waite + degree-3 polynomial path on the FMA pipe instead of MUFU.EX2 (|rel err| < 7.5e-5, far below the
         // 16-bit rounding of P).  The argument never exceeds 8 (exact max, lazy reference), so only the lower end is
         // clamped (-inf for masked columns; below -125 the exponent add would leave the normal range).
-        auto exp_half = [&](auto half_tag, const float (&s)[16], const float neg, uint32_t (&pk8)[8], float2& sum) {
+        auto exp_half = [&](auto half_tag, auto spec_tag, const float (&s)[16], const float neg, uint32_t (&pk8)[8], float2& sum) {
             constexpr int kHalf = decltype(half_tag)::value;         // pairs [4 kHalf, 4 kHalf + 4) of the chunk's 8
+            constexpr bool kSpec = decltype(spec_tag)::value;        // speculative step: the argument is not bounded above
             const float2 c2v = make_float2(c2, c2);
             const float2 negv = make_float2(neg, neg);
             // kEmu -> emulated pairs of every 8 (spread evenly): 4 -> {0}, 1 -> {0,4}, 3 -> {0,3,6}, 2 -> {0,2,4,6}
@@ -317,6 +402,9 @@ flash_fwd_kernel_sm100_p4(const __grid_constant__ CUtensorMap tmQ, const __grid_
                 if (((i * kEmu8) & 7) < kEmu8) {
                     const float2 magic = make_float2(12582912.f, 12582912.f);       // 1.5 * 2^23
                     x = make_float2(fmaxf(x.x, -125.f), fmaxf(x.y, -125.f));
+                    // above 126 the exponent add below would wrap around (2^141 came out as -2^-116 in round 1): clamped,
+                    // the value is ~2^126 and trips the overflow check of the speculative step like MUFU's +inf does
+                    if constexpr (kSpec) x = make_float2(fminf(x.x, 126.f), fminf(x.y, 126.f));
                     const float2 tt = __fadd2_rn(x, magic);                                   // low mantissa bits = rint(x)
                     const float2 nnf = __ffma2_rn(tt, make_float2(-1.f, -1.f), magic);        // -rint(x), exact
                     const float2 f = __fadd2_rn(x, nnf);                                      // x - rint(x) in [-0.5, 0.5]
@@ -355,6 +443,12 @@ flash_fwd_kernel_sm100_p4(const __grid_constant__ CUtensorMap tmQ, const __grid_
         int tr_step = 0;
         const int erole = (hh == 0 && wq == 0) ? 6 + t : 99;   // rows 6 / 7: epilogue stamps of warp 0 of tile 0 / 1, one row per item
         (void)trole; (void)tr_step; (void)erole;
+        // own sum of step j, truncated to its top 16 bits, into half (j & 1) of the own exchange slot
+        auto publish_sum = [&](const int j, const float2& sum) {
+            hs16 = __float_as_uint(sum.x + sum.y) >> 16;
+            asm volatile("st.shared.u16 [%0], %1;" ::"r"(x_own + ((j & 1) << 1)), "h"((uint16_t)hs16) : "memory");
+        };
+        constexpr float kOverflowAt = kBf16 ? 1.2676506e30f /* 2^100 */ : 32768.f /* fp16 P <= 65504 */;
         // A quarter of P leaves in two steps: the TMEM store is issued as soon as the chunk's exponentials are done, the
         // hand-over to the MMA warp (wait::st, fence, one elected arrive per warp) half a chunk later, underneath the next
         // chunk's exponentials.  Waiting for the store right behind its issue cost ~130 cycles per quarter with both warps
@@ -368,7 +462,11 @@ flash_fwd_kernel_sm100_p4(const __grid_constant__ CUtensorMap tmQ, const __grid_
             if (lane == 0) FA_TRACE_EVENT(trole, tr_step, 2 + q);
         };
 
-        for (int n = blockIdx.x; n < ts.total; n += gridDim.x) {
+        for (int pass = 0; pass < 2; ++pass) {
+          const bool safe = pass == 1 || exact0;     // exact steps only (pass 1 redoes the items whose speculation overflowed)
+          const int cnt = pass_count(pass);
+          for (int idx = 0; idx < cnt; ++idx) {
+            const int n = pass_item(pass, idx);
             // Only what the key loop needs stays live across it (n_t, the first step that needs a mask, the thread's column
             // limit): with 104 registers and no L1 (shared memory takes all of it) every spilled value is an L2 round trip.
             // The epilogue decodes the item again.
@@ -400,10 +498,19 @@ flash_fwd_kernel_sm100_p4(const __grid_constant__ CUtensorMap tmQ, const __grid_
                 if (p.is_causal) first_masked = min(first_masked, (mt + g.causal_off + 1) / kBlockN);
                 j_mask = max(first_masked, 0);
             }
-            float m_ref = -INFINITY, l_run = 0.f;
+            // softmax state of the row: reference exponent neg = -m_ref * c2 (identical in both threads of the row), own partial sum
+            float neg = 0.f, l_run = 0.f;
+            bool has_ref = false;
+            hs16 = 0;
+            int* pz = &poison[2 * t + (nitem & 1)];
 
+            // ------------------------------------------------------------------------------------------------------
+            // exact step: row max first (pass 1), then the exponentials.  Every step of a retried item, and the first
+            // step of every item.
+            // ------------------------------------------------------------------------------------------------------
             auto key_step = [&](auto mask_tag, const int j) {
                 constexpr bool need_mask = decltype(mask_tag)::value;   // masked and unmasked steps get separate straight-line copies
+                using spec = std::false_type;
                 tr_step = its + j;
                 const int lim = lim0 - j * kBlockN;            // last visible column of this thread's 64 (may be < 0 or >= 64)
                 if (j == 0 && (tid & 31) == 0) FA_TRACE_EVENT(trole, its, 7);   // first step of an item: about to wait for its S
@@ -414,14 +521,6 @@ flash_fwd_kernel_sm100_p4(const __grid_constant__ CUtensorMap tmQ, const __grid_
                 // ---- pass 1: exact row max of the 64 own scores; chunk 0 stays in registers for pass 2 ----
                 float sa[16];
                 float mx;
-#if FA_P4_EXPERIMENT_NOMAX   // TIMING EXPERIMENT ONLY (wrong for data whose row max grows after the first key tile)
-                if (j > 0) {
-                    tmem_ld16(tS, *reinterpret_cast<uint32_t(*)[16]>(&sa[0]));
-                    tmem_wait_ld();
-                    if constexpr (need_mask) mask_chunk(sa, lim);
-                    mx = m_ref;
-                } else
-#endif
                 {
 #if FA_P4_PASS1_WIDE
                     float sc[16], sd[16], sb[16];
@@ -449,25 +548,27 @@ flash_fwd_kernel_sm100_p4(const __grid_constant__ CUtensorMap tmQ, const __grid_
                     mx = fmaxf(mx, max_chunk(sa));
 #endif
                 }
-#if FA_P4_EXPERIMENT_NOMAX
-                if (j == 0)
-#endif
                 {
                     sts32f(x_own, mx);
                     named_bar_sync(pair_bar, 64);
                     float mp;
                     asm volatile("ld.shared.f32 %0, [%1];" : "=f"(mp) : "r"(x_own ^ (kBlockM * 4)));
                     mx = fmaxf(mx, mp);
+                    // the 16-bit halves of this slot carry the speculative steps' sums: nobody may publish into it before
+                    // both threads of the row have read the maxima
+                    named_bar_sync(pair_bar, 64);
                 }
                 if ((tid & 31) == 0) FA_TRACE_EVENT(trole, its + j, 1);
-                // lazy reference: it moves only when the row max grew by more than 2^8 (always on the first visible key)
-                const bool need = (mx - m_ref) * c2 > kRescaleThreshold;
+                // lazy reference: it moves only when the row max is more than 2^8 above it (always on the first visible key)
+                const float xm = fmaf(mx, c2, neg);
+                const bool need = has_ref ? (xm > kRescaleThreshold) : (mx > -INFINITY);
                 if (__any_sync(0xffffffffu, need)) {
                     // both warps of the pair take this path together (they see the same 32 row maxima)
                     float alpha = 1.f;
                     if (need) {
-                        alpha = fast_exp2((m_ref - mx) * c2);        // 0 when there was no reference yet
-                        m_ref = mx;
+                        alpha = has_ref ? fast_exp2(-xm) : 0.f;      // 2^((m_old - m_new) c2); nothing accumulated yet without a reference
+                        neg = -mx * c2;
+                        has_ref = true;
                         l_run *= alpha;
                     }
                     if (j > 0) {
@@ -488,7 +589,6 @@ flash_fwd_kernel_sm100_p4(const __grid_constant__ CUtensorMap tmQ, const __grid_
                         tc_fence_after();
                     }
                 }
-                const float neg = (m_ref == -INFINITY) ? 0.f : -m_ref * c2;
 
                 // ---- pass 2: exponentials; the next chunk's scores are in flight, the previous quarter's hand-over is folded in ----
                 float2 sum = make_float2(0.f, 0.f);
@@ -496,45 +596,133 @@ flash_fwd_kernel_sm100_p4(const __grid_constant__ CUtensorMap tmQ, const __grid_
                     float sb[16];
                     uint32_t pka[8], pkb[8];
                     tmem_ld16(tS + 16, *reinterpret_cast<uint32_t(*)[16]>(&sb[0]));
-                    exp_half(h0{}, sa, neg, pka, sum);
-                    exp_half(h1{}, sa, neg, pka, sum);
+                    exp_half(h0{}, spec{}, sa, neg, pka, sum);
+                    exp_half(h1{}, spec{}, sa, neg, pka, sum);
                     tmem_st8(tS, pka);
                     tmem_wait_ld();
                     tmem_ld16(tS + 32, *reinterpret_cast<uint32_t(*)[16]>(&sa[0]));
                     if constexpr (need_mask) mask_chunk(sb, lim - 16);
-                    exp_half(h0{}, sb, neg, pkb, sum);
+                    exp_half(h0{}, spec{}, sb, neg, pkb, sum);
                     arrive_quarter(0);
-                    exp_half(h1{}, sb, neg, pkb, sum);
+                    exp_half(h1{}, spec{}, sb, neg, pkb, sum);
                     tmem_st8(tS + 8, pkb);
                     tmem_wait_ld();
                     tmem_ld16(tS + 48, *reinterpret_cast<uint32_t(*)[16]>(&sb[0]));
                     if constexpr (need_mask) mask_chunk(sa, lim - 32);
-                    exp_half(h0{}, sa, neg, pka, sum);
+                    exp_half(h0{}, spec{}, sa, neg, pka, sum);
                     arrive_quarter(1);
-                    exp_half(h1{}, sa, neg, pka, sum);
+                    exp_half(h1{}, spec{}, sa, neg, pka, sum);
                     tmem_st8(tS + 16, pka);
                     tmem_wait_ld();
                     if constexpr (need_mask) mask_chunk(sb, lim - 48);
-                    exp_half(h0{}, sb, neg, pkb, sum);
+                    exp_half(h0{}, spec{}, sb, neg, pkb, sum);
                     arrive_quarter(2);
-                    exp_half(h1{}, sb, neg, pkb, sum);
+                    exp_half(h1{}, spec{}, sb, neg, pkb, sum);
+                    publish_sum(j, sum);                  // before the last hand-over: the peer reads it after the next S is full
                     tmem_st8(tS + 24, pkb);
                     arrive_quarter(3);
                 }
                 l_run += sum.x + sum.y;
             };
+
+            // ------------------------------------------------------------------------------------------------------
+            // speculative step ("late-agreed reference"): no pass 1, no exchange on the critical path.  The exponentials
+            // use the reference agreed so far; the two threads of a row publish their step sums and read each other's ONE
+            // STEP LATE: if the row's sum of step j-1 exceeded 2^9 both shift the reference up by floor(log2 sum) (identical
+            // arithmetic on identical inputs -> identical reference, no vote) and rescale their half of O and their partial
+            // l — an exact power of two.  What cannot be fixed one step late is an overflow inside a single key tile
+            // (bf16: a row sum above 2^100, fp16: above 2^15, i.e. scores jumping by that much within 128 keys): the thread
+            // flags the item, its rows come out as garbage, and the CTA redoes the whole item with exact steps in pass 1.
+            // ------------------------------------------------------------------------------------------------------
+            auto spec_step = [&](auto mask_tag, const int j) {
+                constexpr bool need_mask = decltype(mask_tag)::value;
+                using spec = std::true_type;
+                tr_step = its + j;
+                const int lim = lim0 - j * kBlockN;
+                mbar_wait(&bar_s_full[t], (its + j) & 1);
+                tc_fence_after();
+                if ((tid & 31) == 0) FA_TRACE_EVENT(trole, its + j, 0);
+                float sa[16], sb[16];
+                tmem_ld16(tS, *reinterpret_cast<uint32_t(*)[16]>(&sa[0]));
+                tmem_ld16(tS + 16, *reinterpret_cast<uint32_t(*)[16]>(&sb[0]));
+                {   // late agreement on the reference (underneath the TMEM loads)
+                    uint32_t peer16;
+                    asm volatile("ld.shared.u16 %0, [%1];" : "=r"(peer16) : "r"((x_own ^ (kBlockM * 4)) + (((j - 1) & 1) << 1)));
+                    const float tot = __uint_as_float(hs16 << 16) + __uint_as_float(peer16 << 16);
+                    const bool up = tot > 512.f;
+                    if (__any_sync(0xffffffffu, up)) {
+                        int e = 0;
+                        if (up) e = min((int)((__float_as_uint(tot) >> 23) & 0xffu) - 127, 120);   // floor(log2 tot); inf / garbage: the row is flagged anyway
+                        const float sc = __uint_as_float((uint32_t)(127 - e) << 23);              // 2^-e
+                        neg -= (float)e;
+                        l_run *= sc;
+                        tmem_wait_ld();
+#pragma unroll 1
+                        for (int c = 0; c < kHalfD / 16; ++c) {
+                            uint32_t o[16];
+                            tmem_ld16(tO + c * 16, o);
+                            tmem_wait_ld();
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * sc);
+                            tmem_st16(tO + c * 16, o);
+                        }
+                        tmem_wait_st();
+                        tc_fence_before();
+                        named_bar_sync(pair_bar, 64);      // P V of this step accumulates into all of O_t: both halves rescaled first
+                        tc_fence_after();
+                    }
+                }
+                if ((tid & 31) == 0) FA_TRACE_EVENT(trole, its + j, 1);
+                float2 sum = make_float2(0.f, 0.f);
+                {
+                    uint32_t pka[8], pkb[8];
+                    tmem_wait_ld();
+                    if constexpr (need_mask) mask_chunk(sa, lim);
+                    exp_half(h0{}, spec{}, sa, neg, pka, sum);
+                    exp_half(h1{}, spec{}, sa, neg, pka, sum);
+                    tmem_st8(tS, pka);
+                    tmem_ld16(tS + 32, *reinterpret_cast<uint32_t(*)[16]>(&sa[0]));
+                    if constexpr (need_mask) mask_chunk(sb, lim - 16);
+                    exp_half(h0{}, spec{}, sb, neg, pkb, sum);
+                    arrive_quarter(0);
+                    exp_half(h1{}, spec{}, sb, neg, pkb, sum);
+                    tmem_st8(tS + 8, pkb);
+                    tmem_wait_ld();
+                    tmem_ld16(tS + 48, *reinterpret_cast<uint32_t(*)[16]>(&sb[0]));
+                    if constexpr (need_mask) mask_chunk(sa, lim - 32);
+                    exp_half(h0{}, spec{}, sa, neg, pka, sum);
+                    arrive_quarter(1);
+                    exp_half(h1{}, spec{}, sa, neg, pka, sum);
+                    tmem_st8(tS + 16, pka);
+                    tmem_wait_ld();
+                    if constexpr (need_mask) mask_chunk(sb, lim - 48);
+                    exp_half(h0{}, spec{}, sb, neg, pkb, sum);
+                    arrive_quarter(2);
+                    exp_half(h1{}, spec{}, sb, neg, pkb, sum);
+                    publish_sum(j, sum);
+                    tmem_st8(tS + 24, pkb);
+                    arrive_quarter(3);
+                }
+                const float hs = sum.x + sum.y;
+                // overflow (also inf / NaN), or no reference yet (only an exact step can establish one; with prefix masks a row
+                // that saw no key in the first tile sees none at all and never gets here with more than one key step)
+                if (!(hs <= kOverflowAt) || (!has_ref && hs != 0.f)) *reinterpret_cast<volatile int*>(pz) = 1;
+                l_run += hs;
+            };
             for (int j = 0; j < n_t; ++j) {
-                if (j >= j_mask) key_step(std::true_type{}, j);
-                else key_step(std::false_type{}, j);
+                if (safe || j == 0) {
+                    if (j >= j_mask) key_step(std::true_type{}, j);
+                    else key_step(std::false_type{}, j);
+                } else {
+                    if (j >= j_mask) spec_step(std::true_type{}, j);
+                    else spec_step(std::false_type{}, j);
+                }
             }
             its += n_t;
 
-            // ---- epilogue: O_t / l -> 16 bit -> staging tile (128B-swizzled, the TMA layout) -> TMA store ----
+            // ---- epilogue: O_t / l -> 16 bit -> staging tile (128B-swizzled, the TMA layout) -> TMA store by warp 18 + t ----
             if ((tid & 31) == 0) FA_TRACE_EVENT(erole, nitem, 0);     // rows 6 / 7: epilogue of item `nitem` (0 start, 1 O full, 2 l exchanged,
-            mbar_wait(&bar_o_full[t], nitem & 1);                  //   3 staging tile taken, 4 O in registers, 5 staged, 6 handed over)
-            tc_fence_after();
-            if ((tid & 31) == 0) FA_TRACE_EVENT(erole, nitem, 1);
-            int n_again = n;
+            int n_again = n;                                           //   3 staging tile free, 4 O in registers, 5 staged, 6 handed over)
             asm volatile("" : "+r"(n_again));                  // opaque copy: keeps the geometry from living across the key loop
             const WorkItem w = decode_item(ts, n_again, p.h, p.is_causal != 0);
             const ItemGeom g = item_geom(p, w);
@@ -547,11 +735,14 @@ flash_fwd_kernel_sm100_p4(const __grid_constant__ CUtensorMap tmQ, const __grid_
             float l_peer;
             asm volatile("ld.shared.f32 %0, [%1];" : "=f"(l_peer) : "r"(x_own ^ (kBlockM * 4)));
             const float l_tot = l_run + l_peer;
-            const bool row_empty = (m_ref == -INFINITY) || !(l_tot > 0.f);   // no visible key: O = 0, LSE = 0
+            const bool row_empty = !has_ref || !(l_tot > 0.f);   // no visible key: O = 0, LSE = 0
             const float inv_l = row_empty ? 0.f : (1.f / l_tot);
             if ((tid & 31) == 0) FA_TRACE_EVENT(erole, nitem, 2);
-            if (hh == 0 && wq == 0) {    // take the staging tile (the other tile's epilogue may hold it); the whole warp spins
-                int got;                 // together: bar.sync below is warp-aligned
+            mbar_wait(&bar_o_full[t], nitem & 1);
+            tc_fence_after();
+            if ((tid & 31) == 0) FA_TRACE_EVENT(erole, nitem, 1);
+            if (hh == 0 && wq == 0) {    // take the staging tile (the other tile's store may still be reading it); the whole warp
+                int got;                 // spins together: bar.sync below is warp-aligned
                 do {
                     got = 0;
                     if (lane == 0) got = (atomicCAS(stage_lock, 0, 1) == 0);
@@ -584,30 +775,41 @@ flash_fwd_kernel_sm100_p4(const __grid_constant__ CUtensorMap tmQ, const __grid_
                     sts128u(stage + (chunk >> 3) * L::kSlab + r_in_tile * 128 + (((chunk & 7) ^ (r_in_tile & 7)) << 4), v);
                 }
             }
-            if (hh == 0 && row < g.sq_b) lse_row[row] = row_empty ? 0.f : (m_ref * p.scale + logf(l_tot));
+            if (hh == 0 && row < g.sq_b) lse_row[row] = row_empty ? 0.f : fmaf(-neg, 0.6931471805599453f, logf(l_tot));   // m_ref / sqrt(d) + ln l
             if ((tid & 31) == 0) FA_TRACE_EVENT(erole, nitem, 5);
             fence_proxy_async_smem();                          // generic-proxy writes -> visible to the TMA engine
             const bool whole_tile = (mt + kBlockM <= g.sq_b) || (p.cu_q == nullptr);   // dense: TMA clips rows >= seqlen_q itself
             if (whole_tile) {
-                named_bar_arrive(11 + t, 2 * kBlockM + 32);    // hand the staging tile to store warp 18 + t (it releases the lock) and move on
+                // hand the tile to store warp 18 + t and move on: it checks the overflow flag, issues the bulk store and
+                // releases the staging tile once the engine has read it
+                named_bar_arrive(11 + t, 2 * kBlockM + 32);
             } else {
                 // ragged varlen tail: a TMA box would spill into the next sequence -> predicated coalesced stores
                 constexpr int kChunksPerRow = D / 8;
                 named_bar_sync(tile_bar, 2 * kBlockM);
-                for (int idx = hh * kBlockM + r_in_tile; idx < kBlockM * kChunksPerRow; idx += 2 * kBlockM) {
-                    const int rr = idx / kChunksPerRow, ch = idx % kChunksPerRow;
+                for (int idx2 = hh * kBlockM + r_in_tile; idx2 < kBlockM * kChunksPerRow; idx2 += 2 * kBlockM) {
+                    const int rr = idx2 / kChunksPerRow, ch = idx2 % kChunksPerRow;
                     if (mt + rr < g.sq_b) {
                         const uint4 v = lds128u(stage + (ch >> 3) * L::kSlab + rr * 128 + (((ch & 7) ^ (rr & 7)) << 4));
                         *(reinterpret_cast<uint4*>(o_base + ((o_row_base + mt + rr) * p.h + w.bidh) * D) + ch) = v;
                     }
                 }
                 named_bar_sync(tile_bar, 2 * kBlockM);
-                if (hh == 0 && r_in_tile == 0) atomicExch(stage_lock, 0);
+                if (hh == 0 && r_in_tile == 0) {
+                    if (*reinterpret_cast<volatile int*>(pz)) {       // (the store warp does this for whole tiles)
+                        *reinterpret_cast<volatile int*>(pz) = 0;
+                        const int k2 = atomicAdd(retry_count, 1);
+                        if (k2 < kMaxRetry) retry_list[k2] = n;
+                    }
+                    atomicExch(stage_lock, 0);
+                }
                 __syncwarp();
             }
             if ((tid & 31) == 0) FA_TRACE_EVENT(trole, its - 1, 6);
             if ((tid & 31) == 0) FA_TRACE_EVENT(erole, nitem, 6);
             ++nitem;
+          }
+          if (pass == 0) { pass_boundary(); if (pass_count(1) == 0) break; }
         }
     }
 

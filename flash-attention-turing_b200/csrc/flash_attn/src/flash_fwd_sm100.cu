@@ -25,7 +25,8 @@ static int fwd_emu(int d) {
         if (v < -1 || v > 4) v = -1;
     }
     if (v >= 0) return v;
-    return d == 128 ? 1 : 2;
+    (void)d;
+    return 0;   // MUFU.EX2 everywhere: with the speculative key steps the polynomial path (range clamps on both ends) no longer pays
 }
 
 template <int D>
@@ -53,6 +54,9 @@ int launch_fwd_sm100(const fa_fwd_params* p, cudaStream_t stream) {
     kp.b = (int)p->b; kp.sq = (int)p->seqlen_q; kp.sk = (int)p->seqlen_k; kp.h = (int)p->h; kp.h_k = (int)p->h_k;
     kp.hratio = (int)(p->h / p->h_k);
     kp.is_causal = p->is_causal;
+    static int exact = -1;   // FA_B200_FWD_EXACT=1: exact row max at every key step (the retry path of the default kernel) for A/B runs
+    if (exact < 0) { const char* e = getenv("FA_B200_FWD_EXACT"); exact = (e && atoi(e) != 0) ? 1 : 0; }
+    kp.exact = exact;
     kp.scale = 1.0f / sqrtf((float)p->d);
     kp.scale_log2 = kp.scale * 1.4426950408889634f;
     kp.inv_scale_log2 = 1.0f / kp.scale_log2;

@@ -32,8 +32,15 @@ def timeit(fn, n):
     return e0.elapsed_time(e1) / n
 
 
-print(f"| seqlen | hdim | causal | flash_fwd_kernel ms | TFLOP/s | flash_bwd (dot+dq+dk_dv) ms | TFLOP/s | torch SDPA fwd ms | speed-up vs SDPA |")
-print("|---|---|---|---|---|---|---|---|---|")
+ref = None
+try:   # the reference's own kernels rebuilt for sm_100a (fp16 only), when staged by baseline/build_ref.sh
+    sys.path.insert(0, os.path.join(ROOT, "baseline", "_ref"))
+    import flash_attn_turing_ref as ref
+except Exception:
+    ref = None
+print(f"benchmark.sh grid (batch {batch_size}, heads {num_heads}), dtype {args.dtype}; CUDA events, device-resident tensors; TFLOP/s algorithmic (bwd = 2.5 x fwd)")
+print(f"| seqlen | hdim | causal | flash_fwd_kernel ms | TFLOP/s | flash_bwd (dot+dq+dk_dv) ms | TFLOP/s | torch SDPA fwd ms | TFLOP/s | torch SDPA bwd ms | TFLOP/s | reference kernels fwd ms | bwd ms |")
+print("|---|---|---|---|---|---|---|---|---|---|---|---|---|")
 for s in seqlens:
     for d in (64, 128):
         for causal in (False, True):
@@ -45,5 +52,15 @@ for s in seqlens:
             tb = timeit(lambda: fat.bwd(q, k, v, o, l, do, causal), max(2, n // 2))
             qt, kt, vt = [t.transpose(1, 2) for t in (q, k, v)]
             ts = timeit(lambda: F.scaled_dot_product_attention(qt, kt, vt, is_causal=causal), n)
+            qg, kg, vg = (t.detach().clone().requires_grad_(True) for t in (qt, kt, vt))
+            og = F.scaled_dot_product_attention(qg, kg, vg, is_causal=causal)
+            dot = do.transpose(1, 2)
+            tsb = timeit(lambda: torch.autograd.grad(og, (qg, kg, vg), dot, retain_graph=True), max(2, n // 2))
             fl = 4 * batch_size * num_heads * s * s * d * (0.5 if causal else 1.0)
-            print(f"| {s} | {d} | {causal} | {tf:.3f} | {fl/tf/1e9:.0f} | {tb:.3f} | {2.5*fl/tb/1e9:.0f} | {ts:.3f} | {ts/tf:.2f}x |", flush=True)
+            rf = rb = float("nan")
+            if ref is not None and dt == torch.float16:
+                ro, rl = ref.fwd(q, k, v, causal)
+                rf = timeit(lambda: ref.fwd(q, k, v, causal), max(2, n // 4))
+                rb = timeit(lambda: ref.bwd(q, k, v, ro, rl, do, causal), 2)
+            print(f"| {s} | {d} | {causal} | {tf:.3f} | {fl/tf/1e9:.0f} | {tb:.3f} | {2.5*fl/tb/1e9:.0f} | {ts:.3f} | {fl/ts/1e9:.0f} | {tsb:.3f} | {2.5*fl/tsb/1e9:.0f} | {rf:.3f} | {rb:.3f} |", flush=True)
+            del qg, kg, vg, og
