@@ -262,10 +262,273 @@ flash_fwd_kernel_sm100_p4(const __grid_constant__ CUtensorMap tmQ, const __grid_
                 if (nb1 > 0) { mbar_wait(&bar_q_full[1], nitem[1] & 1); issue_s(1, 0, nb1); }
                 commit(&bar_kv_empty[kv_slot(0)]);
                 bool v_ready = false;     // V_j was already seen full by the probe of the previous step
+                for (int j = 0; j < nbmax; ++j) {
+                    if (!v_ready) wait_kv(2 * j + 1);  // V_j
+                    v_ready = false;
+                    bool k_ready = false;
+#pragma unroll
+                    for (int t = 0; t < 2; ++t) {
+                        const int nbt = t == 0 ? nb0 : nb1;
+                        if (j < nbt) {
+                            if (j == 0) {   // O_t of the previous item must have been read out by its epilogue
+                                mbar_wait(&bar_o_empty[t], (nitem[t] & 1) ^ 1);
+                            }
+                            // The softmax warps hand P over quarter by quarter, in order.  When this warp gets here late (the
+                            // usual case: it was issuing the other tile's MMAs) all four quarters are there already, and four
+                            // waits on completed barriers (~90-200 cycles each with the sub-partition's softmax warps competing
+                            // for issue slots) let the tensor pipe run dry: probe the LAST quarter first.
+                            if (mbar_test_wait(&bar_p[4 * t + 3], (it[t] + j) & 1)) {
+                                tc_fence_after();
+                                if (lane == 0) FA_TRACE_EVENT(4 + t, it[t] + j, 3);
+#pragma unroll
+                                for (int q = 0; q < 4; ++q) issue_pv(t, j, q);
+                            } else {
+#pragma unroll
+                                for (int q = 0; q < 4; ++q) {
+                                    mbar_wait(&bar_p[4 * t + q], (it[t] + j) & 1);
+                                    tc_fence_after();
+                                    if (lane == 0) FA_TRACE_EVENT(4 + t, it[t] + j, q);      // rows 4 / 5: MMA warp, tile 0 / 1
+                                    issue_pv(t, j, q);
+                                }
+                            }
+                            if (lane == 0) FA_TRACE_EVENT(4 + t, it[t] + j, 4);
+                            if (j + 1 < nbt) {
+                                if (!k_ready) { wait_kv(2 * j + 2); tc_fence_after(); k_ready = true; }
+                                if (lane == 0) FA_TRACE_EVENT(4 + t, it[t] + j, 5);
+                                // probe V_j+1 now, underneath the eight MMAs about to be queued, instead of after them
+                                if (t == 1 && j + 1 < nbmax)
+                                    v_ready = mbar_test_wait(&bar_kv_full[kv_slot(2 * j + 3)], (((kv_i + 2 * j + 3) / kStages) & 1));
+                                issue_s(t, j + 1, nbt);
+                            } else {
+                                commit(&bar_o_full[t]);
+                            }
+                            if (lane == 0) FA_TRACE_EVENT(4 + t, it[t] + j, 6);
+                        }
+                    }
                     commit(&bar_kv_empty[kv_slot(2 * j + 1)]);
                     if (j + 1 < nbmax) commit(&bar_kv_empty[kv_slot(2 * j + 2)]);
                     __syncwarp();
                 }
+                kv_i += 2 * nbmax;
+                it[0] += nb0; it[1] += nb1;
+                nitem[0] += (nb0 > 0); nitem[1] += (nb1 > 0);
+              }
+              if (pass == 0) { pass_boundary(); if (pass_count(1) == 0) break; }
+            }
+        } else {
+            // ===================== warps 18 / 19: TMA store of tile slot 0 / 1 =====================
+            // The softmax warpgroups only write the staging tile and arrive on a named barrier; issuing the bulk store and
+            // waiting for the engine to read 32 KB of shared memory (~1800 cycles) is this warp's job.  When a softmax
+            // thread did it, its whole warp sat in that wait and — every P quarter needs all eight warps of a tile — held
+            // up the tile's first key steps of the next item (clock64: the next item's first S was picked up ~1200 cycles
+            // after the epilogue had finished, profiles/r02_run3.log).
+            const int t = warp - 18;
+            int nit = 0;                                           // items in which this tile had keys (= the softmax warps' nitem)
+            for (int pass = 0; pass < 2; ++pass) {
+              const int cnt = pass_count(pass);
+              for (int idx = 0; idx < cnt; ++idx) {
+                const int n = pass_item(pass, idx);
+                const WorkItem w = decode_item(ts, n, p.h, p.is_causal != 0);
+                const ItemGeom g = item_geom(p, w);
+                if (g.skip) continue;
+                const int mt = g.m0 + t * kBlockM;
+                if (mt >= g.sq_b || g.nblk[t] == 0) continue;
+                const int par = nit & 1;
+                ++nit;
+                const bool whole_tile = (mt + kBlockM <= g.sq_b) || (p.cu_q == nullptr);
+                if (!whole_tile) continue;                         // ragged varlen tail: stored by the softmax threads themselves
+                named_bar_sync(11 + t, 2 * kBlockM + 32);          // staging tile written and fenced by the tile's 256 threads
+                if (lane == 0) {
+                    if (poison[2 * t + par]) {                     // some row of this tile overflowed its speculative step: redo the item
+                        poison[2 * t + par] = 0;
+                        const int k2 = atomicAdd(retry_count, 1);
+                        if (k2 < kMaxRetry) retry_list[k2] = n;
+                    }
+#pragma unroll
+                    for (int sl = 0; sl < kSlabs; ++sl)
+                        tma_store_4d(&tmO, sStage + sl * L::kSlab, sl * 64, w.bidh, g.q_row0 + mt, g.tma_b);
+                    tma_store_commit();
+                    tma_store_wait_read<0>();                      // staging tile has been read; global writes complete later
+                    __threadfence_block();
+                    atomicExch(stage_lock, 0);                     // the other tile's epilogue (or this tile's next one) may take it
+                }
+                __syncwarp();
+              }
+              if (lane == 0) tma_store_wait<0>();                  // all bulk stores have landed before a retry rewrites the tile / the CTA retires
+              __syncwarp();
+              if (pass == 0) { pass_boundary(); if (pass_count(1) == 0) break; }
+            }
+        }
+    } else {
+        // ========== softmax warpgroups: warpgroup 2t+hh owns columns [64hh, 64hh+64) of tile slot t, one thread per row ==========
+        // Register budget: five warps per SM sub-partition launch with 96 registers each; setmaxnreg.inc can only draw what
+        // setmaxnreg.dec released (the launch-time slack of the register file is NOT in the pool: a 112/64 split deadlocks,
+        // profiles/r01s2_run1_setmaxnreg_hang.log), so warpgroup 4 gives up 32 per thread and each softmax warp takes 8.
+        setmaxnreg_inc<104>();
+        const int t = wg >> 1;
+        const int hh = wg & 1;
+        const int wq = warp & 3;                         // TMEM lane quadrant = SM sub-partition
+        const int r_in_tile = tid & 127;
+        const uint32_t lane_base = (uint32_t)(wq * 32) << 16;
+        const uint32_t tS = tmem_base + lane_base + kTmemS0 + t * 128 + hh * 64;       // own scores; own P goes to the same place
+        const uint32_t tO = tmem_base + lane_base + kTmemO0 + t * 128 + hh * kHalfD;   // own half of the O row
+        const uint32_t x_own = xch + ((t * 2 + hh) * kBlockM + r_in_tile) * 4;
+        const uint32_t pair_bar = 1 + t * 4 + wq;       // named barriers 1..8: the two warps that share 32 rows (64 threads)
+        const uint32_t tile_bar = 9 + t;                // named barriers 9, 10: the two warpgroups of a tile (256 threads); 11, 12: + its store warp
+        uint16_t* o_base = reinterpret_cast<uint16_t*>(p.o);
+        const float c2 = p.scale_log2;
+        int its = 0;       // S_t steps so far
+        int nitem = 0;     // items with keys finished by this slot
+        uint32_t hs16 = 0; // own sum of the previous key step, top 16 bits (what the peer thread reads one step late)
+
+        // P = 2^(s*c2 + neg) for one 16-column chunk; kEmu selects how many of every 8 column pairs go through the
+        // Cody-Waite + degree-3 polynomial path on the FMA pipe instead of MUFU.EX2 (|rel err| < 7.5e-5, far below the
+        // 16-bit rounding of P).  The argument never exceeds 8 (exact max, lazy reference), so only the lower end is
+        // clamped (-inf for masked columns; below -125 the exponent add would leave the normal range).
+        auto exp_half = [&](auto half_tag, auto spec_tag, const float (&s)[16], const float neg, uint32_t (&pk8)[8], float2& sum) {
+            constexpr int kHalf = decltype(half_tag)::value;         // pairs [4 kHalf, 4 kHalf + 4) of the chunk's 8
+            constexpr bool kSpec = decltype(spec_tag)::value;        // speculative step: the argument is not bounded above
+            const float2 c2v = make_float2(c2, c2);
+            const float2 negv = make_float2(neg, neg);
+            // kEmu -> emulated pairs of every 8 (spread evenly): 4 -> {0}, 1 -> {0,4}, 3 -> {0,3,6}, 2 -> {0,2,4,6}
+            constexpr int kEmu8 = kEmu == 1 ? 2 : kEmu == 2 ? 4 : kEmu == 3 ? 3 : kEmu == 4 ? 1 : 0;
+#pragma unroll
+            for (int i = 4 * kHalf; i < 4 * kHalf + 4; ++i) {
+                float2 x = __ffma2_rn(make_float2(s[2 * i], s[2 * i + 1]), c2v, negv);
+                float2 pp;
+                if (((i * kEmu8) & 7) < kEmu8) {
+                    const float2 magic = make_float2(12582912.f, 12582912.f);       // 1.5 * 2^23
+                    x = make_float2(fmaxf(x.x, -125.f), fmaxf(x.y, -125.f));
+                    // above 126 the exponent add below would wrap around (2^141 came out as -2^-116 in round 1): clamped,
+                    // the value is ~2^126 and trips the overflow check of the speculative step like MUFU's +inf does
+                    if constexpr (kSpec) x = make_float2(fminf(x.x, 126.f), fminf(x.y, 126.f));
+                    const float2 tt = __fadd2_rn(x, magic);                                   // low mantissa bits = rint(x)
+                    const float2 nnf = __ffma2_rn(tt, make_float2(-1.f, -1.f), magic);        // -rint(x), exact
+                    const float2 f = __fadd2_rn(x, nnf);                                      // x - rint(x) in [-0.5, 0.5]
+                    float2 pl = __ffma2_rn(make_float2(0.05517115816473961f, 0.05517115816473961f), f,
+                                           make_float2(0.2426101416349411f, 0.2426101416349411f));
+                    pl = __ffma2_rn(pl, f, make_float2(0.6932609677314758f, 0.6932609677314758f));
+                    pl = __ffma2_rn(pl, f, make_float2(0.9999281167984009f, 0.9999281167984009f));
+                    pp = make_float2(__uint_as_float(__float_as_uint(pl.x) + (__float_as_uint(tt.x) << 23)),
+                                     __uint_as_float(__float_as_uint(pl.y) + (__float_as_uint(tt.y) << 23)));
+                } else {
+                    pp = make_float2(fast_exp2(x.x), fast_exp2(x.y));
+                }
+                sum = __fadd2_rn(sum, pp);
+                pk8[i] = pack2<kBf16>(pp.x, pp.y);
+            }
+        };
+        using h0 = std::integral_constant<int, 0>;
+        using h1 = std::integral_constant<int, 1>;
+        auto mask_chunk = [&](float (&s)[16], const int lim_c) {
+#pragma unroll
+            for (int c = 0; c < 16; ++c)
+                if (c > lim_c) s[c] = -INFINITY;
+        };
+        auto max_chunk = [&](const float (&s)[16]) -> float {
+            float ma = fmaxf(s[0], s[1]), mb = fmaxf(s[2], s[3]);
+#pragma unroll
+            for (int c = 4; c < 16; c += 4) {
+                ma = fmaxf(ma, fmaxf(s[c], s[c + 1]));
+                mb = fmaxf(mb, fmaxf(s[c + 2], s[c + 3]));
+            }
+            return fmaxf(ma, mb);
+        };
+        // clock64 builds: rows 0 / 1 = warp 0 of tile 0 / 1 (column half 0, lane quadrant 0), rows 2 / 3 = warp 7 of the tile
+        // (column half 1, quadrant 3); events 0 S full, 1 max exchanged, 2..5 quarter q handed over, 6 O full, 7 epilogue done
+        const int trole = (hh == 0 && wq == 0) ? t : (hh == 1 && wq == 3) ? 2 + t : 99;
+        int tr_step = 0;
+        const int erole = (hh == 0 && wq == 0) ? 6 + t : 99;   // rows 6 / 7: epilogue stamps of warp 0 of tile 0 / 1, one row per item
+        (void)trole; (void)tr_step; (void)erole;
+        // own sum of step j, truncated to its top 16 bits, into half (j & 1) of the own exchange slot
+        auto publish_sum = [&](const int j, const float2& sum) {
+            hs16 = __float_as_uint(sum.x + sum.y) >> 16;
+            asm volatile("st.shared.u16 [%0], %1;" ::"r"(x_own + ((j & 1) << 1)), "h"((uint16_t)hs16) : "memory");
+        };
+        constexpr float kOverflowAt = kBf16 ? 1.2676506e30f /* 2^100 */ : 32768.f /* fp16 P <= 65504 */;
+        // A quarter of P leaves in two steps: the TMEM store is issued as soon as the chunk's exponentials are done, the
+        // hand-over to the MMA warp (wait::st, fence, one elected arrive per warp) half a chunk later, underneath the next
+        // chunk's exponentials.  Waiting for the store right behind its issue cost ~130 cycles per quarter with both warps
+        // of a sub-partition stalled at the same time and the MUFU pipe idle (clock64: pass 2 took 1520 cycles instead of
+        // ~1000, profiles/r02_run1.log).
+        auto arrive_quarter = [&](const int q) {
+            tmem_wait_st();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bar_p[4 * t + q]);
+            if (lane == 0) FA_TRACE_EVENT(trole, tr_step, 2 + q);
+        };
+
+        for (int pass = 0; pass < 2; ++pass) {
+          const bool safe = pass == 1 || exact0;     // exact steps only (pass 1 redoes the items whose speculation overflowed)
+          const int cnt = pass_count(pass);
+          for (int idx = 0; idx < cnt; ++idx) {
+            const int n = pass_item(pass, idx);
+            // Only what the key loop needs stays live across it (n_t, the first step that needs a mask, the thread's column
+            // limit): with 104 registers and no L1 (shared memory takes all of it) every spilled value is an L2 round trip.
+            // The epilogue decodes the item again.
+            int n_t, j_mask, lim0;
+            {
+                const WorkItem w = decode_item(ts, n, p.h, p.is_causal != 0);
+                const ItemGeom g = item_geom(p, w);
+                if (g.skip) continue;
+                const int mt = g.m0 + t * kBlockM;
+                if (mt >= g.sq_b) continue;                  // this slot has no rows in this item (nblk[t] == 0 too)
+                n_t = g.nblk[t];
+                const int row = mt + r_in_tile;
+                if (n_t == 0) {
+                    // rows exist but see no key: O = 0, LSE = 0 (each half clears its D/2 columns)
+                    if (row < g.sq_b) {
+                        const int64_t o_row_base = (p.cu_q != nullptr) ? (int64_t)g.q_row0 : (int64_t)w.bidb * p.sq;
+                        uint16_t* o_row = o_base + ((o_row_base + row) * p.h + w.bidh) * D + hh * kHalfD;
+#pragma unroll
+                        for (int ch = 0; ch < kHalfD / 8; ++ch) *(reinterpret_cast<uint4*>(o_row) + ch) = make_uint4(0, 0, 0, 0);
+                        if (hh == 0) p.lse[((int64_t)w.bidb * p.h + w.bidh) * p.sq + row] = 0.f;
+                    }
+                    continue;
+                }
+                int col_limit = g.sk_b - 1;                  // last visible key of this row
+                if (p.is_causal) col_limit = min(col_limit, row + g.causal_off);
+                lim0 = col_limit - hh * 64;                  // ... relative to this thread's first column of key tile 0
+                // key tile j needs a mask iff 128 j + 128 > sk_b (tail) or, causal, 128 j + 127 > mt + causal_off (diagonal)
+                int first_masked = g.sk_b / kBlockN;         // floor: tiles below are entirely inside the sequence
+                if (p.is_causal) first_masked = min(first_masked, (mt + g.causal_off + 1) / kBlockN);
+                j_mask = max(first_masked, 0);
+            }
+            // softmax state of the row: reference exponent neg = -m_ref * c2 (identical in both threads of the row), own partial sum
+            float neg = 0.f, l_run = 0.f;
+            bool has_ref = false;
+            hs16 = 0;
+            int* pz = &poison[2 * t + (nitem & 1)];
+
+            // ------------------------------------------------------------------------------------------------------
+            // exact step: row max first (pass 1), then the exponentials.  Every step of a retried item, and the first
+            // step of every item.
+            // ------------------------------------------------------------------------------------------------------
+            auto key_step = [&](auto mask_tag, const int j) {
+                constexpr bool need_mask = decltype(mask_tag)::value;   // masked and unmasked steps get separate straight-line copies
+                using spec = std::false_type;
+                tr_step = its + j;
+                const int lim = lim0 - j * kBlockN;            // last visible column of this thread's 64 (may be < 0 or >= 64)
+                if (j == 0 && (tid & 31) == 0) FA_TRACE_EVENT(trole, its, 7);   // first step of an item: about to wait for its S
+                mbar_wait(&bar_s_full[t], (its + j) & 1);
+                tc_fence_after();
+                if ((tid & 31) == 0) FA_TRACE_EVENT(trole, its + j, 0);
+
+                // ---- pass 1: exact row max of the 64 own scores; chunk 0 stays in registers for pass 2 ----
+                float sa[16];
+                float mx;
+                {
+#if FA_P4_PASS1_WIDE
+                    float sc[16], sd[16], sb[16];
+                    tmem_ld16(tS + 32, *reinterpret_cast<uint32_t(*)[16]>(&sc[0]));
+                    tmem_ld16(tS + 48, *reinterpret_cast<uint32_t(*)[16]>(&sd[0]));
+                    tmem_ld16(tS + 16, *reinterpret_cast<uint32_t(*)[16]>(&sb[0]));
+                    tmem_ld16(tS, *reinterpret_cast<uint32_t(*)[16]>(&sa[0]));
+                    tmem_wait_ld();
+                    if constexpr (need_mask) { mask_chunk(sc, lim - 32); mask_chunk(sd, lim - 48); mask_chunk(sb, lim - 16); mask_chunk(sa, lim); }
+                    mx = fmaxf(fmaxf(max_chunk(sc), max_chunk(sd)), fmaxf(max_chunk(sb), max_chunk(sa)));
+#else
                     float sc[16], sd[16], sb[16];
                     tmem_ld16(tS + 32, *reinterpret_cast<uint32_t(*)[16]>(&sc[0]));
                     tmem_ld16(tS + 48, *reinterpret_cast<uint32_t(*)[16]>(&sd[0]));
@@ -280,6 +543,7 @@ flash_fwd_kernel_sm100_p4(const __grid_constant__ CUtensorMap tmQ, const __grid_
                     tmem_wait_ld();
                     if constexpr (need_mask) mask_chunk(sa, lim);
                     mx = fmaxf(mx, max_chunk(sa));
+#endif
                 }
                 {
                     sts32f(x_own, mx);
