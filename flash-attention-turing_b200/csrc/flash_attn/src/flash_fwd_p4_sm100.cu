@@ -124,14 +124,18 @@ flash_fwd_kernel_sm100_p4(const __grid_constant__ CUtensorMap tmQ, const __grid_
 
     // ---- work list: pass 0 = this CTA's share of the static schedule; pass 1 = the items of pass 0 in which some row's
     // speculative exponentials overflowed (retry list in shared memory), redone with the exact per-step row max ----
-    const int n_static = (ts.total > (int)blockIdx.x) ? (ts.total - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+    const int slots_mine = (ts.total > (int)blockIdx.x) ? (ts.total - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+    const int n_static = ts.paired ? 2 * slots_mine : slots_mine;      // items of this CTA in the static schedule
+    auto static_item = [&](int idx) -> int {                           // idx-th item: slot blockIdx + k gridDim (both halves of a pair)
+        return ts.paired ? 2 * ((int)blockIdx.x + (idx >> 1) * (int)gridDim.x) + (idx & 1) : (int)blockIdx.x + idx * (int)gridDim.x;
+    };
     auto pass_count = [&](int pass) -> int {
         if (pass == 0) return n_static;
         const int c = *reinterpret_cast<volatile int*>(retry_count);
         return c > kMaxRetry ? n_static : c;          // list overflow: redo everything
     };
     auto pass_item = [&](int pass, int idx) -> int {
-        if (pass == 0 || *reinterpret_cast<volatile int*>(retry_count) > kMaxRetry) return (int)blockIdx.x + idx * (int)gridDim.x;
+        if (pass == 0 || *reinterpret_cast<volatile int*>(retry_count) > kMaxRetry) return static_item(idx);
         return reinterpret_cast<volatile int*>(retry_list)[idx];
     };
     // every thread of the CTA calls this once, between the passes (each role from its own branch: barrier 0 counts threads)

@@ -8,45 +8,79 @@ import itertools
 import random
 
 
-def make_tile_sched(b, h, sq, sk, d, group_mb=16):
+def make_tile_sched(b, h, sq, sk, d, group_mb=16, causal=False):
     num_mblk = (sq + 255) // 256
     bh = b * h
     kv_bytes_per_head = 2 * sk * d * 2
     grp = (group_mb << 20) // kv_bytes_per_head if kv_bytes_per_head > 0 else bh
     grp = max(1, min(grp, bh))
-    return {"num_mblk": num_mblk, "bh": bh, "group": grp, "total": num_mblk * bh}
+    levels = (num_mblk + 1) // 2 if causal else num_mblk          # causal: a slot pairs row blocks L and num_mblk - 1 - L
+    return {"num_mblk": num_mblk, "levels": levels, "paired": causal, "bh": bh, "group": grp, "total": levels * bh}
 
 
 def decode_item(ts, n, h, causal):
-    per_group = ts["group"] * ts["num_mblk"]
-    g = n // per_group
-    r = n - g * per_group
+    half, slot = (n & 1, n >> 1) if ts["paired"] else (0, n)
+    per_group = ts["group"] * ts["levels"]
+    g = slot // per_group
+    r = slot - g * per_group
     heads_here = min(ts["group"], ts["bh"] - g * ts["group"])
     level = r // heads_here
     head_local = r - level * heads_here
     bhi = g * ts["group"] + head_local
-    mblk = (ts["num_mblk"] - 1 - level) if causal else level
+    if ts["paired"]:
+        heavy = ts["num_mblk"] - 1 - level
+        mblk = heavy if half == 0 else (level if level < heavy else ts["num_mblk"])   # num_mblk = void item
+    else:
+        mblk = level
     return mblk, bhi % h, bhi // h
+
+
+def cta_items(ts, cta, grid):
+    """the static schedule of one CTA (flash_fwd_p4_sm100.cu: static_item)"""
+    slots = range(cta, ts["total"], grid)
+    return [2 * s + half for s in slots for half in (0, 1)] if ts["paired"] else list(slots)
 
 
 def test_forward_work_list_covers_every_tile_pair_exactly_once():
     random.seed(0)
     shapes = [(4, 32, 4096, 4096, 128), (4, 32, 8192, 8192, 128), (1, 1, 1, 1, 128), (3, 6, 129, 127, 64),
-              (2, 4, 1025, 1, 128), (256, 32, 16384, 16384, 128)]
+              (2, 4, 1025, 1, 128), (256, 32, 16384, 16384, 128), (1, 2, 768, 768, 128)]
     shapes += [(random.randint(1, 9), random.randint(1, 33), random.randint(1, 5000), random.randint(1, 70000),
                 random.choice([64, 128])) for _ in range(200)]
     for (b, h, sq, sk, d), causal, mb in itertools.product(shapes, (False, True), (1, 16, 4096)):
         if b * h * ((sq + 255) // 256) > 300000:
             b = 2                                   # keep the enumeration small; the formulas do not depend on b's size
-        ts = make_tile_sched(b, h, sq, sk, d, mb)
+        ts = make_tile_sched(b, h, sq, sk, d, mb, causal)
         seen = set()
-        for n in range(ts["total"]):
-            item = decode_item(ts, n, h, causal)
-            mblk, bidh, bidb = item
-            assert 0 <= mblk < ts["num_mblk"] and 0 <= bidh < h and 0 <= bidb < b, (item, ts)
-            assert item not in seen, f"duplicate {item} for {(b, h, sq, sk, d, causal, mb)}"
-            seen.add(item)
+        grid = min(ts["total"], 148)
+        for cta in range(grid):
+            for n in cta_items(ts, cta, grid):
+                item = decode_item(ts, n, h, causal)
+                mblk, bidh, bidb = item
+                if mblk == ts["num_mblk"]:
+                    continue                        # void second half of an unpaired middle block
+                assert 0 <= mblk < ts["num_mblk"] and 0 <= bidh < h and 0 <= bidb < b, (item, ts)
+                assert item not in seen, f"duplicate {item} for {(b, h, sq, sk, d, causal, mb)}"
+                seen.add(item)
         assert len(seen) == ts["num_mblk"] * b * h
+
+
+def test_causal_schedule_is_balanced():
+    """paired causal slots all cost 2 * num_mblk + 2 key steps (sq == sk): per-CTA sums differ by at most one slot"""
+    for (b, h, s) in [(4, 32, 8192), (4, 16, 16384), (1, 7, 4096), (2, 3, 2048 + 256)]:
+        ts = make_tile_sched(b, h, s, s, 128, 16, True)
+        grid = min(ts["total"], 148)
+        cost = []
+        for cta in range(grid):
+            c = 0
+            for n in cta_items(ts, cta, grid):
+                mblk, _, _ = decode_item(ts, n, h, True)
+                if mblk < ts["num_mblk"]:
+                    c += nblk(mblk * 256, s, s, True) + nblk(mblk * 256 + 128, s, s, True)
+            cost.append(c)
+        per_slot = 4 * ts["num_mblk"] + 2 if ts["num_mblk"] % 2 == 0 else None
+        if per_slot:
+            assert max(cost) - min(cost) <= per_slot, (b, h, s, min(cost), max(cost))
 
 
 def nblk(mt, sq_b, sk_b, causal):
