@@ -3,34 +3,36 @@
 // Replaces the reference's compute_attn_1rowblock (/root/reference/csrc/flash_attn/src/flash_fwd_kernel.h:23-789).
 //
 // One CTA per SM walks a static list of work items; one item = two 128-row query tiles of one (batch, head), key tiles
-// of 128.  TMEM: S0 S1 (fp32 scores, 128 columns each), O0 O1 (fp32 accumulators, head_dim columns each).  The MMA warp
-// issues   S0 S1 | PV0 S0' | PV1 S1' | ...   — the tensor pipe is in-order, so "S_t' complete" implies "PV_t complete".
+// of 128.  TMEM: S0 S1 (fp32 scores, 128 columns each), O0 O1 (fp32 accumulators, head_dim columns each).  Tensor-pipe
+// order   S0 S1 | PV0 S0' | PV1 S1' | ...   — in order per issuing thread, so "S_t' complete" implies "PV_t complete".
 //
 // Roles (640 threads): warpgroup 2t+hh = softmax of tile t, key columns [64hh, 64hh+64), one thread per query row
-//                      (104 registers/thread); warp 16 = MMA issuer, warp 17 = TMA producer (64 registers/thread).
+//                      (104 registers/thread); warp 16 / 17 = MMA issuer of tile 0 / 1 (they pass a token so that the
+//                      tiles' blocks of MMAs alternate), warp 18 = TMA producer, warp 19 = TMA store of the O tiles
+//                      (64 registers/thread).  A 21st warp does not fit the register file of a sub-partition.
 // Why two threads per row: the exponentials of a 128x128 tile need 1024 cycles of the SM's MUFU units (16 ex2/clk), as
 // long as the tile's two MMAs, and a tile's dependency loop is S_t -> softmax_t -> P_t V -> S_t'; the two tiles' softmax
 // phases mostly alternate, and ONE warp per SM sub-partition cannot keep the MUFU pipe full on its own (measured 1430
 // cycles per row-tile against 1050-1150 with two, profiles/r01_ubench_softmax_pipes.log).
 //
-// Round-2 loop (this file).  The round-1 loop (speculative exponentials + a vote on the tile sum AFTER them) released
-// P_t only once all 128 columns were done: clock64 showed 1680 cycles from "S_t full" to "P_t released" and then 1270
-// until S_t' was back (1024 of them MMA) — 2940 cycles per pair of tiles against 2048 of MMA work, the softmax warps
-// waiting on S-full 39 % of the time (profiles/r01s2_trace_fwd_p4.log, ncu source page).  Now:
-//   1. pass 1: exact row max of the thread's 64 scores (all four 16-column chunks loaded at once), exchanged with the
-//      peer thread of the row through a 4-byte shared-memory slot and a 64-thread named barrier.  Both threads see the
-//      same max, so the lazy-rescale decision (reference moves only when the max grows by > 2^8) needs no vote and the
-//      exponentials below can never overflow: no speculation, no redo path, no clamp on the polynomial's upper range.
-//   2. pass 2: exponentials chunk by chunk; each chunk's 8 packed P columns are stored to TMEM and RELEASED AT ONCE
-//      (one mbarrier per tile and 16-column quarter, one elected arrive per warp).  The MMA warp issues P V in the same
-//      order — k-steps (q, 4+q) for quarter q: chunk q of both column halves — so three quarters of P V run underneath
-//      the remaining exponentials and only 128 + 512 cycles of MMA (last quarter + next S) follow the last release.
-// P quarter q of half hh overwrites columns [64hh + 8q, +8) of S_t, which both passes have consumed by then.
+// Key loop of a softmax thread (details at key_step / spec_step below):
+//   * exact step (first step of an item, every step of a retried item): row max of the thread's 64 scores, exchanged with
+//     the peer thread of the row through a 4-byte shared-memory slot and a 64-thread named barrier; lazy reference (moves
+//     only when the max grows by > 2^8); then the exponentials.
+//   * speculative step (all others): exponentials against the reference agreed so far; the two threads of a row publish
+//     their step sums and read each other's one step late ("late-agreed reference"); an overflow inside one key tile flags
+//     the item and the CTA redoes it with exact steps in a second pass.
+//   * P leaves in four 16-column quarters per thread (TMEM store, then one elected arrive per warp half a chunk later);
+//     the MMA warp issues P V in the same order, k-steps (q, 4+q) for quarter q.
+// P quarter q of half hh overwrites columns [64hh + 8q, +8) of S_t, which have been consumed by then.
 #include <atomic>
 #include <type_traits>
 
 #include "flash_fwd_common.cuh"
 
+#ifndef FA_P4_MMA2
+#define FA_P4_MMA2 1         // 1: one MMA-issuing warp per query tile, strict block alternation through a token (see the MMA section)
+#endif
 #ifndef FA_P4_PASS1_WIDE
 #define FA_P4_PASS1_WIDE 0   // 1: pass 1 loads all four score chunks at once (64 registers in flight) instead of 32 + 16 + 16
 #endif
@@ -38,8 +40,12 @@
 namespace fa100 {
 
 namespace {
-constexpr int kThreadsP4 = 640;
-constexpr int kMaxRetry = 48;
+constexpr int kThreadsP4 = 640;                        // a 21st warp does not fit: a sub-partition holds 4 x 104 x 32 + 64 x 32 of its 16384 registers
+constexpr int kMma1Warp = FA_P4_MMA2 ? 17 : -1;        // second MMA issuer (tile 1)
+constexpr int kProducerWarp = FA_P4_MMA2 ? 18 : 17;   // TMA producer
+constexpr int kStoreWarp0 = FA_P4_MMA2 ? 19 : 18;     // FA_P4_MMA2: ONE store warp (19) for both tiles (the staging tile is shared anyway)
+static_assert(kStoreWarp0 >= 18, "warp roles");
+constexpr int kMaxRetry = 40;
 template <int D> struct P4Smem {
     static constexpr int kSlab = kBlockM * 128;          // 64-column slab of a 128-row tile: 16 KB
     static constexpr int kSlabs = D / 64;
@@ -90,11 +96,13 @@ flash_fwd_kernel_sm100_p4(const __grid_constant__ CUtensorMap tmQ, const __grid_
     uint64_t* bar_p = bar_s_full + 2;                 // [2 tiles][4 quarters], 8 arrivals each (one per softmax warp of the tile)
     uint64_t* bar_o_full = bar_p + 8;                 // [2]  last P V of the item retired
     uint64_t* bar_o_empty = bar_o_full + 2;           // [2]  epilogue has O_t in registers (8 arrivals)
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_o_empty + 2);
+    uint64_t* bar_tok = bar_o_empty + 2;              // [2]  FA_P4_MMA2: "tile t's MMA warp may issue its next block"
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_tok + 2);
     int* stage_lock = reinterpret_cast<int*>(tmem_slot + 1);   // the two tiles' epilogues share one staging tile
     int* retry_count = stage_lock + 1;                // items whose speculative pass overflowed (see "late-agreed reference")
     int* poison = stage_lock + 2;                     // [2 tiles][2 item parities]: some row of the tile overflowed in this item
     int* retry_list = stage_lock + 6;                 // [kMaxRetry] work-item indices, deduplicated at the pass boundary
+    int* store_desc = retry_list + kMaxRetry;         // FA_P4_MMA2: what the staging tile holds {head, first row, batch, item, 2 t + item parity}
     const uint32_t xch = smem_u32(smem + L::kOffXch);
 
     if (warp == 16) {
@@ -108,13 +116,15 @@ flash_fwd_kernel_sm100_p4(const __grid_constant__ CUtensorMap tmQ, const __grid_
                 for (int q = 0; q < 4; ++q) mbar_init(&bar_p[4 * t + q], 8);
                 mbar_init(&bar_o_full[t], 1); mbar_init(&bar_o_empty[t], 8);
             }
-            for (int i = 0; i < kStages; ++i) { mbar_init(&bar_kv_full[i], 1); mbar_init(&bar_kv_empty[i], 1); }
+            // K/V slots are released by the MMA warp(s): with one issuing warp per tile both have to let go
+            for (int i = 0; i < kStages; ++i) { mbar_init(&bar_kv_full[i], 1); mbar_init(&bar_kv_empty[i], FA_P4_MMA2 ? 2 : 1); }
+            mbar_init(&bar_tok[0], 1); mbar_init(&bar_tok[1], 1);
             fence_barrier_init();
         }
         __syncwarp();
         tmem_alloc<512>(tmem_slot);
         tmem_relinquish();
-    } else if (warp == 17 && lane == 0) {
+    } else if (warp == kProducerWarp && lane == 0) {
         tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV); tma_prefetch_desc(&tmO);
     }
     tc_fence_before();
@@ -160,7 +170,7 @@ flash_fwd_kernel_sm100_p4(const __grid_constant__ CUtensorMap tmQ, const __grid_
 
     if (wg == 4) {
         setmaxnreg_dec<64>();
-        if (warp == 17) {
+        if (warp == kProducerWarp) {
             // ===================== TMA producer =====================
             int kv_i = 0;            // running K/V ring index
             int nq[2] = {0, 0};      // Q_t loads so far
@@ -204,6 +214,147 @@ flash_fwd_kernel_sm100_p4(const __grid_constant__ CUtensorMap tmQ, const __grid_
               __syncwarp();
               if (pass == 0) { pass_boundary(); if (pass_count(1) == 0) break; }
             }
+#if FA_P4_MMA2
+        } else if (warp == 16 || warp == kMma1Warp) {
+            // ===================== MMA issuers: warp 16 -> tile 0, warp 17 -> tile 1 =====================
+            // The tensor pipe work of a key step is two BLOCKS, (tile 0: four P quarters + next S) (tile 1: ...), strictly
+            // alternating: that order keeps the two tiles half a period apart — one in its softmax while the other's MMAs
+            // run.  With ONE issuing warp (round 2, first half) clock64 showed 350-550 cycles between the last MMA of a block
+            // and the first of the next: issue blocks while more than 2-3 MMAs are queued, so the warp comes back with
+            // < 200 cycles of work in the pipe and then has three commits, a V wait, the P probe and the descriptor
+            // arithmetic to get through — the pipe ran dry once per block (period 2 x (1024 + 350), tensor pipe 65 % busy).
+            // Now every tile has its own issuing warp that does all its waiting IN ADVANCE and then waits for a token the
+            // other warp passes on right behind its last MMA (mbarrier arrive -> try_wait wake-up).  Without the token
+            // (tried in round 2, profiles/r02_run5.log) the tiles drift into the same phase: 3760 cycles per period.
+            // Block order inside an item: (0,0) (1,0) (0,1) (1,1) ...; tile t has nb_t blocks, so
+            //   (0,j) waits for (1,j-1) iff j >= 1 and j-1 < nb1, and wakes (1,j) iff j < nb1;
+            //   (1,j) waits for (0,j) iff j < nb0, and wakes (0,j+1) iff j+1 < nb0;
+            // the two warps meet on a named barrier at the end of every item (a token may never be passed twice before it
+            // has been picked up: the mbarrier phase parity would alias).
+            const int t = (warp == 16) ? 0 : 1;
+            const bool leader = elect_one();
+            constexpr uint32_t idesc_s = make_idesc(kBf16, kBlockM, kBlockN, false, false);
+            constexpr uint32_t idesc_pv = make_idesc(kBf16, kBlockM, D, false, true);
+            const uint32_t tm = __shfl_sync(0xffffffffu, tmem_base, 0);
+            const uint32_t q_lo = __shfl_sync(0xffffffffu, desc_lo(smem_u32(sQ), 16), 0);
+            const uint32_t kv_lo = __shfl_sync(0xffffffffu, desc_lo(smem_u32(sKV), 16), 0);
+            const uint32_t v_lo = __shfl_sync(0xffffffffu, desc_lo(smem_u32(sKV), L::kSlab), 0);
+            constexpr uint32_t kTile16 = L::kTile >> 4;
+            int kv_i = 0;                 // ring index of K_0 of the current item
+            int its = 0;                  // S_t / P_t steps so far (barrier parities)
+            int nitem = 0;                // items in which this tile had keys (Q / O barrier parities)
+            int ntok = 0;                 // tokens picked up so far
+            for (int pass = 0; pass < 2; ++pass) {
+              const int cnt = pass_count(pass);
+              for (int idx = 0; idx < cnt; ++idx) {
+                const int n = pass_item(pass, idx);
+                const WorkItem w = decode_item(ts, n, p.h, p.is_causal != 0);
+                const ItemGeom g = item_geom(p, w);
+                const int nb0 = __shfl_sync(0xffffffffu, g.nblk[0], 0);
+                const int nb1 = __shfl_sync(0xffffffffu, g.nblk[1], 0);
+                const int nbmax = max(nb0, nb1);
+                if (__shfl_sync(0xffffffffu, (int)g.skip, 0) || nbmax == 0) continue;
+                const int nbt = t == 0 ? nb0 : nb1;
+                auto kv_slot = [&](int i) { return (kv_i + i) % kStages; };
+                auto wait_kv = [&](int i) { mbar_wait(&bar_kv_full[kv_slot(i)], (((kv_i + i) / kStages) & 1)); };
+                auto commit = [&](uint64_t* bar) { if (leader) tc_commit(bar); };
+                // S_t = Q_t K_j^T, then the token.  Passing it a few MMAs BEFORE the end of the block (so that the other warp's
+                // first MMAs queue up right behind this block's last ones) measured much slower — C2 1121 instead of 1356
+                // TFLOP/s, profiles/r02_run17.log: with MMAs of two warps in flight at the same time every MMA took ~145
+                // cycles instead of 64 (clock64; the pipe seems to alternate between the issuing warps and drain in between).
+                auto issue_s = [&](int j, bool give) {
+                    if (leader) {
+                        const uint32_t qa = q_lo + t * kTile16;
+                        const uint32_t ka = kv_lo + kv_slot(2 * j) * kTile16;
+#pragma unroll
+                        for (int kk = 0; kk < D / 16; ++kk) {
+                            const uint32_t off = ((kk >> 2) * L::kSlab + (kk & 3) * 32) >> 4;
+                            umma_ss(tm + kTmemS0 + t * 128, desc_make(qa + off, kDescHiK), desc_make(ka + off, kDescHiK),
+                                    idesc_s, kk > 0);
+                        }
+                        if (give) mbar_arrive(&bar_tok[t ^ 1]);
+                        tc_commit(&bar_s_full[t]);
+                    }
+                };
+                // O_t += P_t[:, quarter q] V_j[quarter q]: key rows [16q, 16q+16) (P written by half 0) and
+                // [64+16q, 64+16q+16) (half 1); P quarter (hh, q) sits at S_t + 64 hh + 8 q
+                auto issue_pv = [&](int j, int q) {
+                    if (leader) {
+                        const uint32_t va = v_lo + kv_slot(2 * j + 1) * kTile16;
+#pragma unroll
+                        for (int hh = 0; hh < 2; ++hh)
+                            umma_ts(tm + kTmemO0 + t * 128, tm + kTmemS0 + t * 128 + hh * 64 + q * 8,
+                                    desc_make(va + (hh * 4 + q) * (2048 >> 4), kDescHiK), idesc_pv, (j > 0 || q > 0 || hh > 0));
+                    }
+                };
+                if (nbt > 0) {
+                    wait_kv(0);
+                    mbar_wait(&bar_q_full[t], nitem & 1);
+                    tc_fence_after();
+                    issue_s(0, false);
+                    if (nbt == 1) commit(&bar_q_empty[t]);          // Q_t may be overwritten by the next item
+                    commit(&bar_kv_empty[kv_slot(0)]);
+                }
+                for (int j = 0; j < nbt; ++j) {
+                    // everything this block needs, before asking for the token
+                    wait_kv(2 * j + 1);                                             // V_j
+                    if (j + 1 < nbt) wait_kv(2 * j + 2);                            // K_j+1
+                    if (j == 0) mbar_wait(&bar_o_empty[t], (nitem & 1) ^ 1);        // O_t of the previous item has been read out
+                    const bool take = (t == 0) ? (j >= 1 && j - 1 < nb1) : (j < nb0);
+                    if (take) { mbar_wait(&bar_tok[t], ntok & 1); ++ntok; }
+                    // The softmax warps hand P over quarter by quarter, in order.  When all four are there (the usual case)
+                    // one probe of the last quarter replaces four waits.
+                    // The softmax warps hand P over quarter by quarter, in order.  When all four are there one probe of the
+                    // last quarter replaces four waits.  (Issuing "as many quarters as are ready" back to back, or the first
+                    // quarter before the token, measured 7-9 % SLOWER, profiles/r02_run18.log: P V MMAs that run underneath
+                    // the tile's own remaining exponentials compete with its TMEM loads and stores.  Handing P over only
+                    // once per key step: 1-5 % slower, r02_run19.log.)
+                    const bool give = (t == 0) ? (j < nb1) : (j + 1 < nb0);
+                    const bool last = j + 1 == nbt;
+                    if (mbar_test_wait(&bar_p[4 * t + 3], (its + j) & 1)) {
+                        tc_fence_after();
+                        if (lane == 0) FA_TRACE_EVENT(4 + t, its + j, 3);
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) issue_pv(j, q);
+                    } else {
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            mbar_wait(&bar_p[4 * t + q], (its + j) & 1);
+                            tc_fence_after();
+                            if (lane == 0) FA_TRACE_EVENT(4 + t, its + j, q);      // rows 4 / 5: MMA warp of tile 0 / 1
+                            issue_pv(j, q);
+                        }
+                    }
+                    if (last && give && leader) mbar_arrive(&bar_tok[t ^ 1]);       // last block of the tile: no S follows
+                    if (lane == 0) FA_TRACE_EVENT(4 + t, its + j, 4);
+                    if (!last) {
+                        issue_s(j + 1, give);
+                    } else {
+                        commit(&bar_o_full[t]);
+                    }
+                    if (lane == 0) FA_TRACE_EVENT(4 + t, its + j, 6);
+                    if (j + 2 == nbt) commit(&bar_q_empty[t]);                      // S_t of the last step issued
+                    commit(&bar_kv_empty[kv_slot(2 * j + 1)]);
+                    if (j + 1 < nbt) commit(&bar_kv_empty[kv_slot(2 * j + 2)]);
+                    __syncwarp();
+                }
+                // K/V tiles only the other query tile needs (causal diagonal, ragged tails): let go of them in ring order,
+                // each only once it has landed — its slot's previous release is complete by then
+                for (int j = nbt; j < nbmax; ++j) {
+                    wait_kv(2 * j);
+                    if (leader) mbar_arrive(&bar_kv_empty[kv_slot(2 * j)]);
+                    wait_kv(2 * j + 1);
+                    if (leader) mbar_arrive(&bar_kv_empty[kv_slot(2 * j + 1)]);
+                    __syncwarp();
+                }
+                kv_i += 2 * nbmax;
+                its += nbt;
+                nitem += (nbt > 0);
+                named_bar_sync(13, 64);                                             // the two issuing warps leave an item together
+              }
+              if (pass == 0) { pass_boundary(); if (pass_count(1) == 0) break; }
+            }
+#else
         } else if (warp == 16) {
             // ===================== MMA issuer (warp-uniform walk, one elected lane issues) =====================
             // ONE warp issues for both tiles, strictly alternating (tile 0: four P quarters + next S) (tile 1: ...).  That
@@ -267,7 +418,9 @@ flash_fwd_kernel_sm100_p4(const __grid_constant__ CUtensorMap tmQ, const __grid_
                 commit(&bar_kv_empty[kv_slot(0)]);
                 bool v_ready = false;     // V_j was already seen full by the probe of the previous step
                 for (int j = 0; j < nbmax; ++j) {
+                    if (lane == 0) FA_TRACE_EVENT(4, it[0] + j, 0);      // trace: loop top / V_j there (rows 4: events 0, 1)
                     if (!v_ready) wait_kv(2 * j + 1);  // V_j
+                    if (lane == 0) FA_TRACE_EVENT(4, it[0] + j, 1);
                     v_ready = false;
                     bool k_ready = false;
 #pragma unroll
@@ -281,6 +434,7 @@ flash_fwd_kernel_sm100_p4(const __grid_constant__ CUtensorMap tmQ, const __grid_
                             // usual case: it was issuing the other tile's MMAs) all four quarters are there already, and four
                             // waits on completed barriers (~90-200 cycles each with the sub-partition's softmax warps competing
                             // for issue slots) let the tensor pipe run dry: probe the LAST quarter first.
+                            if (lane == 0) FA_TRACE_EVENT(4 + t, it[t] + j, 7);  // trace: about to probe
                             if (mbar_test_wait(&bar_p[4 * t + 3], (it[t] + j) & 1)) {
                                 tc_fence_after();
                                 if (lane == 0) FA_TRACE_EVENT(4 + t, it[t] + j, 3);
@@ -319,14 +473,58 @@ flash_fwd_kernel_sm100_p4(const __grid_constant__ CUtensorMap tmQ, const __grid_
               }
               if (pass == 0) { pass_boundary(); if (pass_count(1) == 0) break; }
             }
+#endif
         } else {
-            // ===================== warps 18 / 19: TMA store of tile slot 0 / 1 =====================
+            // ===================== store warp(s): TMA store of the staged O tiles =====================
             // The softmax warpgroups only write the staging tile and arrive on a named barrier; issuing the bulk store and
             // waiting for the engine to read 32 KB of shared memory (~1800 cycles) is this warp's job.  When a softmax
             // thread did it, its whole warp sat in that wait and — every P quarter needs all eight warps of a tile — held
             // up the tile's first key steps of the next item (clock64: the next item's first S was picked up ~1200 cycles
             // after the epilogue had finished, profiles/r02_run3.log).
-            const int t = warp - 18;
+#if FA_P4_MMA2
+            // One warp serves both tiles: whoever holds the staging lock describes the tile in store_desc and arrives on
+            // barrier 11; this warp only has to know HOW MANY whole tiles the CTA's items produce in this pass.
+            for (int pass = 0; pass < 2; ++pass) {
+              const int cnt = pass_count(pass);
+              int n_store = 0;
+              for (int idx = 0; idx < cnt; ++idx) {
+                const int n = pass_item(pass, idx);
+                const WorkItem w = decode_item(ts, n, p.h, p.is_causal != 0);
+                const ItemGeom g = item_geom(p, w);
+                if (g.skip) continue;
+#pragma unroll
+                for (int t = 0; t < 2; ++t) {
+                    const int mt = g.m0 + t * kBlockM;
+                    if (mt >= g.sq_b || g.nblk[t] == 0) continue;
+                    n_store += ((mt + kBlockM <= g.sq_b) || (p.cu_q == nullptr)) ? 1 : 0;   // ragged varlen tails are stored by the softmax threads
+                }
+              }
+              for (int i = 0; i < n_store; ++i) {
+                named_bar_sync(11, 2 * kBlockM + 32);              // staging tile written and fenced by a tile's 256 threads
+                if (lane == 0) {
+                    volatile int* sd = store_desc;
+                    const int bidh = sd[0], row0 = sd[1], tb = sd[2], n = sd[3], pzi = sd[4];
+                    if (poison[pzi]) {                             // some row of this tile overflowed its speculative step: redo the item
+                        poison[pzi] = 0;
+                        const int k2 = atomicAdd(retry_count, 1);
+                        if (k2 < kMaxRetry) retry_list[k2] = n;
+                    }
+#pragma unroll
+                    for (int sl = 0; sl < kSlabs; ++sl)
+                        tma_store_4d(&tmO, sStage + sl * L::kSlab, sl * 64, bidh, row0, tb);
+                    tma_store_commit();
+                    tma_store_wait_read<0>();                      // staging tile has been read; global writes complete later
+                    __threadfence_block();
+                    atomicExch(stage_lock, 0);                     // the other tile's epilogue (or this tile's next one) may take it
+                }
+                __syncwarp();
+              }
+              if (lane == 0) tma_store_wait<0>();                  // all bulk stores have landed before a retry rewrites the tile / the CTA retires
+              __syncwarp();
+              if (pass == 0) { pass_boundary(); if (pass_count(1) == 0) break; }
+            }
+#else
+            const int t = warp - kStoreWarp0;
             int nit = 0;                                           // items in which this tile had keys (= the softmax warps' nitem)
             for (int pass = 0; pass < 2; ++pass) {
               const int cnt = pass_count(pass);
@@ -362,6 +560,7 @@ flash_fwd_kernel_sm100_p4(const __grid_constant__ CUtensorMap tmQ, const __grid_
               __syncwarp();
               if (pass == 0) { pass_boundary(); if (pass_count(1) == 0) break; }
             }
+#endif
         }
     } else {
         // ========== softmax warpgroups: warpgroup 2t+hh owns columns [64hh, 64hh+64) of tile slot t, one thread per row ==========
@@ -778,12 +977,23 @@ flash_fwd_kernel_sm100_p4(const __grid_constant__ CUtensorMap tmQ, const __grid_
             }
             if (hh == 0 && row < g.sq_b) lse_row[row] = row_empty ? 0.f : fmaf(-neg, 0.6931471805599453f, logf(l_tot));   // m_ref / sqrt(d) + ln l
             if ((tid & 31) == 0) FA_TRACE_EVENT(erole, nitem, 5);
+#if FA_P4_MMA2
+            if (hh == 0 && r_in_tile == 0) {                   // tell the store warp what the staging tile holds
+                volatile int* sd = store_desc;
+                sd[0] = w.bidh; sd[1] = g.q_row0 + mt; sd[2] = g.tma_b; sd[3] = n_again; sd[4] = 2 * t + (nitem & 1);
+                __threadfence_block();
+            }
+#endif
             fence_proxy_async_smem();                          // generic-proxy writes -> visible to the TMA engine
             const bool whole_tile = (mt + kBlockM <= g.sq_b) || (p.cu_q == nullptr);   // dense: TMA clips rows >= seqlen_q itself
             if (whole_tile) {
-                // hand the tile to store warp 18 + t and move on: it checks the overflow flag, issues the bulk store and
+                // hand the tile to the store warp and move on: it checks the overflow flag, issues the bulk store and
                 // releases the staging tile once the engine has read it
+#if FA_P4_MMA2
+                named_bar_arrive(11, 2 * kBlockM + 32);
+#else
                 named_bar_arrive(11 + t, 2 * kBlockM + 32);
+#endif
             } else {
                 // ragged varlen tail: a TMA box would spill into the next sequence -> predicated coalesced stores
                 constexpr int kChunksPerRow = D / 8;

@@ -26,7 +26,10 @@ static int fwd_emu(int d) {
     }
     if (v >= 0) return v;
     (void)d;
-    return 0;   // MUFU.EX2 everywhere: with the speculative key steps the polynomial path (range clamps on both ends) no longer pays
+    // 1 pair in 8 through the polynomial: with one MMA-issuing warp per tile the softmax phase is on the critical path again and
+    // taking an eighth of the exponentials off the MUFU pipe pays +2.3 % (C2) / +2.4 % (C3) / +2.8 % (head_dim 64) in a
+    // sustained loop; 2 in 8 measures the same, 3 in 8 nothing (profiles/r02_run19.log)
+    return 4;
 }
 
 template <int D>
