@@ -12,11 +12,14 @@ Headline workload (`value`, `config.workload`):
             sustained : C2 again in a >= 2 s loop (the 1 kW power cap governs; fraction of the sustained peak)
             configs   : C3 (b4 s8192 causal), C4fwd, C4bwd (b4 s16384 forward / backward), C5shard (b32 s16384: one
                         rank's slab of config 5)
-  N > 1 : BASELINE.json configs[4] ("C5": b256 s16384 h32 d128 over 8 GPUs): every rank owns an independent b=32 slab
-          (seed 1000 + rank; batch x head problems shard with no collective on the data path), so scaling is "weak" and
-          `value` = all ranks' FLOPs / max-over-ranks device time.  Legs: c2_weak (b=4 per rank, the N=1 headline
-          workload) and shard_io (NCCL scatter of Q/K/V + gather of O/LSE through flash_attn_turing.sharded, timed
-          OUTSIDE the headline region).  The N=1 line's configs.C5shard is the single-GPU point of the same workload.
+  N > 1 : the same C2 workload on every rank (b=4 per rank, seed 1000 + rank; batch x head problems shard with no
+          collective on the data path), so scaling is "weak" in the contract's sense — per-GPU work is the N=1 work — and
+          `value` = all ranks' FLOPs / max-over-ranks device time.  The line also carries
+            configs.C5shard : BASELINE.json configs[4] ("C5": b256 s16384 h32 d128 over 8 GPUs) — every rank runs one
+                        b=32 s=16384 slab (2^31 elements per tensor, ~117 ms per step, power-capped clocks), timed
+                        between barriers, max over ranks, whole-job TFLOP/s; the N=1 line's configs.C5shard is the
+                        single-GPU point of the same per-rank workload, so config 5 has values at N = 1, 2, 4, 8
+            shard_io  : NCCL scatter of Q/K/V + gather of O/LSE through flash_attn_turing.sharded (outside the headline)
 
 Printed JSON (one line, rank 0): the driver contract plus
   roofline     : tensor-bound; achieved = algorithmic FLOPs per launch / mean launch time (CUDA events on the
@@ -210,7 +213,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--config", default=None, choices=list(CONFIGS), help="headline workload (default: C2 at N=1, C5shard at N>1)")
+    ap.add_argument("--config", default=None, choices=list(CONFIGS), help="headline workload (default: C2, per rank)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-legs", action="store_true", help="skip the sustained / other-config legs")
@@ -220,7 +223,7 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    cfg_name = args.config or ("C2" if world == 1 else "C5shard")
+    cfg_name = args.config or "C2"
     b, s, h, d, causal, desc = CONFIGS[cfg_name]
 
     if args.impl == "reference":
@@ -375,7 +378,12 @@ def main():
         else:
             del q, k, v, o, lse
             torch.cuda.empty_cache()
-            legs["c2_weak"], _ = fwd_leg("C2", 20, 5)              # the N=1 headline workload, b=4 per rank
+            if cfg_name != "C5shard":
+                # north_star's multi-GPU configuration: one b=32 s=16384 slab of config 5 per rank (power-capped regime)
+                legs["C5shard"], _ = fwd_leg("C5shard", 10, 2)
+                legs["C5shard"]["note"] = ("config 5 (b256 s16384 over 8 GPUs): per-rank slab b=32; value = all ranks' FLOPs / "
+                                           "max-over-ranks time; compare with configs.C5shard of the N=1 line")
+                torch.cuda.empty_cache()
             # shard I/O: rank 0 holds a whole b = 4*world batch of C2 rows, NCCL scatters Q/K/V and gathers O/LSE
             from flash_attn_turing import sharded
             bb = 4 * world
@@ -461,7 +469,7 @@ def main():
         if sustained:
             line["sustained"] = sustained
         if legs:
-            line["configs" if world == 1 else "legs"] = legs
+            line["configs"] = legs
         if shard_io:
             line["shard_io"] = shard_io
         if e2e:
