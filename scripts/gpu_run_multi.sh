@@ -1,5 +1,5 @@
 #!/bin/bash
-# 2-GPU validation: NCCL shard I/O test, second-device test, bench.py --gpus 2 (C5shard headline + legs)
+# 2-GPU validation: NCCL shard I/O test, second-device test, bench.py --gpus 2 (C2 weak headline, configs.C5shard, shard_io, e2e)
 L=gpurun_out/r02_multi.log
 mkdir -p gpurun_out; : > $L
 nvidia-smi --query-gpu=index,name --format=csv >> $L
@@ -13,7 +13,7 @@ import json
 try:
     j=json.loads([l for l in open('gpurun_out/r02_bench_n2.json').read().strip().splitlines() if l.startswith('{')][-1])
     print('N=2 value', round(j['value'],1), 'ms', round(j['ms_per_step'],3), j['config']['workload'], 'frac', round(j['roofline']['frac'],3), j['roofline']['peak_kind'], j['clocks'])
-    for k,v in j.get('legs',{}).items(): print(k, {x: v.get(x) for x in ('value','ms_per_step','frac_of_burst_peak','clocks')})
+    for k,v in j.get("configs",{}).items(): print(k, {x: v.get(x) for x in ('value','ms_per_step','frac_of_burst_peak','clocks')})
     print('shard_io', j.get('shard_io'))
     print('e2e', {x: j['e2e'][x] for x in ('value','ms_per_step','copy_floor_ms','frac_of_copy_floor','numa_bound')})
 except Exception as e: print('bench parse failed', e)
