@@ -272,6 +272,8 @@ flash_fwd_kernel_sm100_p4(const __grid_constant__ CUtensorMap tmQ, const __grid_
                             umma_ss(tm + kTmemS0 + t * 128, desc_make(qa + off, kDescHiK), desc_make(ka + off, kDescHiK),
                                     idesc_s, kk > 0);
                         }
+                    }
+                    if (leader) {
                         if (give) mbar_arrive(&bar_tok[t ^ 1]);
                         tc_commit(&bar_s_full[t]);
                     }
@@ -302,13 +304,12 @@ flash_fwd_kernel_sm100_p4(const __grid_constant__ CUtensorMap tmQ, const __grid_
                     if (j == 0) mbar_wait(&bar_o_empty[t], (nitem & 1) ^ 1);        // O_t of the previous item has been read out
                     const bool take = (t == 0) ? (j >= 1 && j - 1 < nb1) : (j < nb0);
                     if (take) { mbar_wait(&bar_tok[t], ntok & 1); ++ntok; }
-                    // The softmax warps hand P over quarter by quarter, in order.  When all four are there (the usual case)
-                    // one probe of the last quarter replaces four waits.
                     // The softmax warps hand P over quarter by quarter, in order.  When all four are there one probe of the
                     // last quarter replaces four waits.  (Issuing "as many quarters as are ready" back to back, or the first
                     // quarter before the token, measured 7-9 % SLOWER, profiles/r02_run18.log: P V MMAs that run underneath
                     // the tile's own remaining exponentials compete with its TMEM loads and stores.  Handing P over only
-                    // once per key step: 1-5 % slower, r02_run19.log.)
+                    // once per key step: 1-5 % slower, r02_run19.log.  The token through a hardware named barrier instead of an
+                    // mbarrier, with or without the first quarter waited for ahead of it: -1.2 % ... +0.5 %, r02_run21.log.)
                     const bool give = (t == 0) ? (j < nb1) : (j + 1 < nb0);
                     const bool last = j + 1 == nbt;
                     if (mbar_test_wait(&bar_p[4 * t + 3], (its + j) & 1)) {
