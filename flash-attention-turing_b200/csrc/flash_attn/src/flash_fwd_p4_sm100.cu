@@ -30,9 +30,6 @@
 
 #include "flash_fwd_common.cuh"
 
-#ifndef FA_P4_MMA2
-#define FA_P4_MMA2 1         // 1: one MMA-issuing warp per query tile, strict block alternation through a token (see the MMA section)
-#endif
 #ifndef FA_P4_PASS1_WIDE
 #define FA_P4_PASS1_WIDE 0   // 1: pass 1 loads all four score chunks at once (64 registers in flight) instead of 32 + 16 + 16
 #endif
@@ -41,10 +38,9 @@ namespace fa100 {
 
 namespace {
 constexpr int kThreadsP4 = 640;                        // a 21st warp does not fit: a sub-partition holds 4 x 104 x 32 + 64 x 32 of its 16384 registers
-constexpr int kMma1Warp = FA_P4_MMA2 ? 17 : -1;        // second MMA issuer (tile 1)
-constexpr int kProducerWarp = FA_P4_MMA2 ? 18 : 17;   // TMA producer
-constexpr int kStoreWarp0 = FA_P4_MMA2 ? 19 : 18;     // FA_P4_MMA2: ONE store warp (19) for both tiles (the staging tile is shared anyway)
-static_assert(kStoreWarp0 >= 18, "warp roles");
+constexpr int kMma1Warp = 17;                          // MMA issuer of tile 1 (warp 16: tile 0)
+constexpr int kProducerWarp = 18;                      // TMA producer
+                                                       // warp 19: TMA store of the O tiles (one staging tile, shared by both query tiles)
 constexpr int kMaxRetry = 40;
 template <int D> struct P4Smem {
     static constexpr int kSlab = kBlockM * 128;          // 64-column slab of a 128-row tile: 16 KB
@@ -81,44 +77,45 @@ flash_fwd_kernel_sm100_p4(const __grid_constant__ CUtensorMap tmQ, const __grid_
     const int lane = tid & 31;
     const int wg = warp >> 2;
 
+    // Only 32-bit addresses in the shared window are kept (never the generic base pointer): see smem_u32 in sm100_ptx.cuh.
     extern __shared__ __align__(1024) uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    if (smem - smem_raw > L::kBytes - L::kNeed) { asm volatile("trap;"); }   // cannot happen with a >= 512-byte aligned window
-    uint8_t* sQ = smem + L::kOffQ;
-    uint8_t* sKV = smem + L::kOffKV;
-    uint8_t* sStage = smem + L::kOffStage;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::kOffBars);
-    uint64_t* bar_q_full = bars;                      // [2]  Q_t landed
-    uint64_t* bar_q_empty = bars + 2;                 // [2]  last S_t MMA of the item retired
-    uint64_t* bar_kv_full = bars + 4;                 // [kStages]
-    uint64_t* bar_kv_empty = bars + 4 + kStages;      // [kStages]
-    uint64_t* bar_s_full = bars + 4 + 2 * kStages;    // [2]
-    uint64_t* bar_p = bar_s_full + 2;                 // [2 tiles][4 quarters], 8 arrivals each (one per softmax warp of the tile)
-    uint64_t* bar_o_full = bar_p + 8;                 // [2]  last P V of the item retired
-    uint64_t* bar_o_empty = bar_o_full + 2;           // [2]  epilogue has O_t in registers (8 arrivals)
-    uint64_t* bar_tok = bar_o_empty + 2;              // [2]  FA_P4_MMA2: "tile t's MMA warp may issue its next block"
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_tok + 2);
-    int* stage_lock = reinterpret_cast<int*>(tmem_slot + 1);   // the two tiles' epilogues share one staging tile
-    int* retry_count = stage_lock + 1;                // items whose speculative pass overflowed (see "late-agreed reference")
-    int* poison = stage_lock + 2;                     // [2 tiles][2 item parities]: some row of the tile overflowed in this item
-    int* retry_list = stage_lock + 6;                 // [kMaxRetry] work-item indices, deduplicated at the pass boundary
-    int* store_desc = retry_list + kMaxRetry;         // FA_P4_MMA2: what the staging tile holds {head, first row, batch, item, 2 t + item parity}
-    const uint32_t xch = smem_u32(smem + L::kOffXch);
+    const uint32_t smem = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    if (smem - smem_u32(smem_raw) > (uint32_t)(L::kBytes - L::kNeed)) { asm volatile("trap;"); }   // cannot happen with a >= 512-byte aligned window
+    const uint32_t sQ = smem + L::kOffQ;
+    const uint32_t sKV = smem + L::kOffKV;
+    const uint32_t sStage = smem + L::kOffStage;
+    const uint32_t bars = smem + L::kOffBars;             // mbarriers, 8 bytes each: bar_x + 8 i
+    const uint32_t bar_q_full = bars;                     // [2]  Q_t landed
+    const uint32_t bar_q_empty = bars + 8 * 2;            // [2]  last S_t MMA of the item retired
+    const uint32_t bar_kv_full = bars + 8 * 4;            // [kStages]
+    const uint32_t bar_kv_empty = bar_kv_full + 8 * kStages;   // [kStages]
+    const uint32_t bar_s_full = bar_kv_empty + 8 * kStages;    // [2]
+    const uint32_t bar_p = bar_s_full + 8 * 2;            // [2 tiles][4 quarters], 8 arrivals each (one per softmax warp of the tile)
+    const uint32_t bar_o_full = bar_p + 8 * 8;            // [2]  last P V of the item retired
+    const uint32_t bar_o_empty = bar_o_full + 8 * 2;      // [2]  epilogue has O_t in registers (8 arrivals)
+    const uint32_t bar_tok = bar_o_empty + 8 * 2;         // [2]  "tile t's MMA warp may issue its next block"
+    const uint32_t tmem_slot = bar_tok + 8 * 2;           // 32-bit words from here on
+    const uint32_t stage_lock = tmem_slot + 4;            // the two tiles' epilogues share one staging tile
+    const uint32_t retry_count = stage_lock + 4;          // items whose speculative pass overflowed (see "late-agreed reference")
+    const uint32_t poison = stage_lock + 8;               // [2 tiles][2 item parities]: some row of the tile overflowed in this item
+    const uint32_t retry_list = stage_lock + 24;          // [kMaxRetry] work-item indices, deduplicated at the pass boundary
+    const uint32_t store_desc = retry_list + 4 * kMaxRetry;   // what the staging tile holds {head, first row, batch, item, 2 t + item parity}
+    const uint32_t xch = smem + L::kOffXch;
 
     if (warp == 16) {
         if (lane == 0) {
-            *stage_lock = 0;
-            *retry_count = 0;
-            poison[0] = poison[1] = poison[2] = poison[3] = 0;
+            sts32(stage_lock, 0);
+            sts32(retry_count, 0);
+            for (int i = 0; i < 4; ++i) sts32(poison + 4 * i, 0);
             for (int t = 0; t < 2; ++t) {
-                mbar_init(&bar_q_full[t], 1); mbar_init(&bar_q_empty[t], 1);
-                mbar_init(&bar_s_full[t], 1);
-                for (int q = 0; q < 4; ++q) mbar_init(&bar_p[4 * t + q], 8);
-                mbar_init(&bar_o_full[t], 1); mbar_init(&bar_o_empty[t], 8);
+                mbar_init(bar_q_full + 8 * (t), 1); mbar_init(bar_q_empty + 8 * (t), 1);
+                mbar_init(bar_s_full + 8 * (t), 1);
+                for (int q = 0; q < 4; ++q) mbar_init(bar_p + 8 * (4 * t + q), 8);
+                mbar_init(bar_o_full + 8 * (t), 1); mbar_init(bar_o_empty + 8 * (t), 8);
             }
             // K/V slots are released by the MMA warp(s): with one issuing warp per tile both have to let go
-            for (int i = 0; i < kStages; ++i) { mbar_init(&bar_kv_full[i], 1); mbar_init(&bar_kv_empty[i], FA_P4_MMA2 ? 2 : 1); }
-            mbar_init(&bar_tok[0], 1); mbar_init(&bar_tok[1], 1);
+            for (int i = 0; i < kStages; ++i) { mbar_init(bar_kv_full + 8 * (i), 1); mbar_init(bar_kv_empty + 8 * (i), 2); }
+            mbar_init(bar_tok + 8 * (0), 1); mbar_init(bar_tok + 8 * (1), 1);
             fence_barrier_init();
         }
         __syncwarp();
@@ -130,7 +127,7 @@ flash_fwd_kernel_sm100_p4(const __grid_constant__ CUtensorMap tmQ, const __grid_
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tmem_base = (uint32_t)lds32(tmem_slot);
 
     // ---- work list: pass 0 = this CTA's share of the static schedule; pass 1 = the items of pass 0 in which some row's
     // speculative exponentials overflowed (retry list in shared memory), redone with the exact per-step row max ----
@@ -141,27 +138,27 @@ flash_fwd_kernel_sm100_p4(const __grid_constant__ CUtensorMap tmQ, const __grid_
     };
     auto pass_count = [&](int pass) -> int {
         if (pass == 0) return n_static;
-        const int c = *reinterpret_cast<volatile int*>(retry_count);
+        const int c = lds32(retry_count);
         return c > kMaxRetry ? n_static : c;          // list overflow: redo everything
     };
     auto pass_item = [&](int pass, int idx) -> int {
-        if (pass == 0 || *reinterpret_cast<volatile int*>(retry_count) > kMaxRetry) return static_item(idx);
-        return reinterpret_cast<volatile int*>(retry_list)[idx];
+        if (pass == 0 || lds32(retry_count) > kMaxRetry) return static_item(idx);
+        return lds32(retry_list + 4 * idx);
     };
     // every thread of the CTA calls this once, between the passes (each role from its own branch: barrier 0 counts threads)
     auto pass_boundary = [&]() {
         __syncthreads();
         if (tid == 0) {
-            const int c = *retry_count;
+            const int c = lds32(retry_count);
             if (c <= kMaxRetry) {                     // both tiles of an item may have queued it: keep one copy
                 int m = 0;
                 for (int i = 0; i < c; ++i) {
-                    const int v = retry_list[i];
+                    const int v = lds32(retry_list + 4 * i);
                     bool dup = false;
-                    for (int k2 = 0; k2 < m; ++k2) dup = dup || (retry_list[k2] == v);
-                    if (!dup) retry_list[m++] = v;
+                    for (int k2 = 0; k2 < m; ++k2) dup = dup || (lds32(retry_list + 4 * k2) == v);
+                    if (!dup) { sts32(retry_list + 4 * m, v); ++m; }
                 }
-                *retry_count = m;
+                sts32(retry_count, m);
             }
         }
         __syncthreads();
@@ -185,19 +182,19 @@ flash_fwd_kernel_sm100_p4(const __grid_constant__ CUtensorMap tmQ, const __grid_
                     const int bidh_k = w.bidh / p.hratio;
                     auto load_kv = [&](const CUtensorMap* tm, int j) {
                         const int slot = kv_i % kStages;
-                        mbar_wait(&bar_kv_empty[slot], ((kv_i / kStages) & 1) ^ 1);
-                        mbar_arrive_expect_tx(&bar_kv_full[slot], L::kTile);
+                        mbar_wait(bar_kv_empty + 8 * (slot), ((kv_i / kStages) & 1) ^ 1);
+                        mbar_arrive_expect_tx(bar_kv_full + 8 * (slot), L::kTile);
                         for (int s = 0; s < kSlabs; ++s)
-                            tma_load_4d(sKV + slot * L::kTile + s * L::kSlab, tm, &bar_kv_full[slot], s * 64, bidh_k,
+                            tma_load_4d(sKV + slot * L::kTile + s * L::kSlab, tm, bar_kv_full + 8 * (slot), s * 64, bidh_k,
                                         g.k_row0 + j * kBlockN, g.tma_b);
                         ++kv_i;
                     };
                     auto load_q = [&](int t) {
                         if (g.nblk[t] == 0) return;
-                        mbar_wait(&bar_q_empty[t], (nq[t] & 1) ^ 1);
-                        mbar_arrive_expect_tx(&bar_q_full[t], L::kTile);
+                        mbar_wait(bar_q_empty + 8 * (t), (nq[t] & 1) ^ 1);
+                        mbar_arrive_expect_tx(bar_q_full + 8 * (t), L::kTile);
                         for (int s = 0; s < kSlabs; ++s)
-                            tma_load_4d(sQ + t * L::kTile + s * L::kSlab, &tmQ, &bar_q_full[t], s * 64, w.bidh,
+                            tma_load_4d(sQ + t * L::kTile + s * L::kSlab, &tmQ, bar_q_full + 8 * (t), s * 64, w.bidh,
                                         g.q_row0 + g.m0 + t * kBlockM, g.tma_b);
                         ++nq[t];
                     };
@@ -214,7 +211,6 @@ flash_fwd_kernel_sm100_p4(const __grid_constant__ CUtensorMap tmQ, const __grid_
               __syncwarp();
               if (pass == 0) { pass_boundary(); if (pass_count(1) == 0) break; }
             }
-#if FA_P4_MMA2
         } else if (warp == 16 || warp == kMma1Warp) {
             // ===================== MMA issuers: warp 16 -> tile 0, warp 17 -> tile 1 =====================
             // The tensor pipe work of a key step is two BLOCKS, (tile 0: four P quarters + next S) (tile 1: ...), strictly
@@ -236,9 +232,9 @@ flash_fwd_kernel_sm100_p4(const __grid_constant__ CUtensorMap tmQ, const __grid_
             constexpr uint32_t idesc_s = make_idesc(kBf16, kBlockM, kBlockN, false, false);
             constexpr uint32_t idesc_pv = make_idesc(kBf16, kBlockM, D, false, true);
             const uint32_t tm = __shfl_sync(0xffffffffu, tmem_base, 0);
-            const uint32_t q_lo = __shfl_sync(0xffffffffu, desc_lo(smem_u32(sQ), 16), 0);
-            const uint32_t kv_lo = __shfl_sync(0xffffffffu, desc_lo(smem_u32(sKV), 16), 0);
-            const uint32_t v_lo = __shfl_sync(0xffffffffu, desc_lo(smem_u32(sKV), L::kSlab), 0);
+            const uint32_t q_lo = __shfl_sync(0xffffffffu, desc_lo(sQ, 16), 0);
+            const uint32_t kv_lo = __shfl_sync(0xffffffffu, desc_lo(sKV, 16), 0);
+            const uint32_t v_lo = __shfl_sync(0xffffffffu, desc_lo(sKV, L::kSlab), 0);
             constexpr uint32_t kTile16 = L::kTile >> 4;
             int kv_i = 0;                 // ring index of K_0 of the current item
             int its = 0;                  // S_t / P_t steps so far (barrier parities)
@@ -256,8 +252,8 @@ flash_fwd_kernel_sm100_p4(const __grid_constant__ CUtensorMap tmQ, const __grid_
                 if (__shfl_sync(0xffffffffu, (int)g.skip, 0) || nbmax == 0) continue;
                 const int nbt = t == 0 ? nb0 : nb1;
                 auto kv_slot = [&](int i) { return (kv_i + i) % kStages; };
-                auto wait_kv = [&](int i) { mbar_wait(&bar_kv_full[kv_slot(i)], (((kv_i + i) / kStages) & 1)); };
-                auto commit = [&](uint64_t* bar) { if (leader) tc_commit(bar); };
+                auto wait_kv = [&](int i) { mbar_wait(bar_kv_full + 8 * (kv_slot(i)), (((kv_i + i) / kStages) & 1)); };
+                auto commit = [&](uint32_t bar) { if (leader) tc_commit(bar); };
                 // S_t = Q_t K_j^T, then the token.  Passing it a few MMAs BEFORE the end of the block (so that the other warp's
                 // first MMAs queue up right behind this block's last ones) measured much slower — C2 1121 instead of 1356
                 // TFLOP/s, profiles/r02_run17.log: with MMAs of two warps in flight at the same time every MMA took ~145
@@ -274,8 +270,8 @@ flash_fwd_kernel_sm100_p4(const __grid_constant__ CUtensorMap tmQ, const __grid_
                         }
                     }
                     if (leader) {
-                        if (give) mbar_arrive(&bar_tok[t ^ 1]);
-                        tc_commit(&bar_s_full[t]);
+                        if (give) mbar_arrive(bar_tok + 8 * (t ^ 1));
+                        tc_commit(bar_s_full + 8 * (t));
                     }
                 };
                 // O_t += P_t[:, quarter q] V_j[quarter q]: key rows [16q, 16q+16) (P written by half 0) and
@@ -291,19 +287,19 @@ flash_fwd_kernel_sm100_p4(const __grid_constant__ CUtensorMap tmQ, const __grid_
                 };
                 if (nbt > 0) {
                     wait_kv(0);
-                    mbar_wait(&bar_q_full[t], nitem & 1);
+                    mbar_wait(bar_q_full + 8 * (t), nitem & 1);
                     tc_fence_after();
                     issue_s(0, false);
-                    if (nbt == 1) commit(&bar_q_empty[t]);          // Q_t may be overwritten by the next item
-                    commit(&bar_kv_empty[kv_slot(0)]);
+                    if (nbt == 1) commit(bar_q_empty + 8 * (t));          // Q_t may be overwritten by the next item
+                    commit(bar_kv_empty + 8 * (kv_slot(0)));
                 }
                 for (int j = 0; j < nbt; ++j) {
                     // everything this block needs, before asking for the token
                     wait_kv(2 * j + 1);                                             // V_j
                     if (j + 1 < nbt) wait_kv(2 * j + 2);                            // K_j+1
-                    if (j == 0) mbar_wait(&bar_o_empty[t], (nitem & 1) ^ 1);        // O_t of the previous item has been read out
+                    if (j == 0) mbar_wait(bar_o_empty + 8 * (t), (nitem & 1) ^ 1);        // O_t of the previous item has been read out
                     const bool take = (t == 0) ? (j >= 1 && j - 1 < nb1) : (j < nb0);
-                    if (take) { mbar_wait(&bar_tok[t], ntok & 1); ++ntok; }
+                    if (take) { mbar_wait(bar_tok + 8 * (t), ntok & 1); ++ntok; }
                     // The softmax warps hand P over quarter by quarter, in order.  When all four are there one probe of the
                     // last quarter replaces four waits.  (Issuing "as many quarters as are ready" back to back, or the first
                     // quarter before the token, measured 7-9 % SLOWER, profiles/r02_run18.log: P V MMAs that run underneath
@@ -312,7 +308,7 @@ flash_fwd_kernel_sm100_p4(const __grid_constant__ CUtensorMap tmQ, const __grid_
                     // mbarrier, with or without the first quarter waited for ahead of it: -1.2 % ... +0.5 %, r02_run21.log.)
                     const bool give = (t == 0) ? (j < nb1) : (j + 1 < nb0);
                     const bool last = j + 1 == nbt;
-                    if (mbar_test_wait(&bar_p[4 * t + 3], (its + j) & 1)) {
+                    if (mbar_test_wait(bar_p + 8 * (4 * t + 3), (its + j) & 1)) {
                         tc_fence_after();
                         if (lane == 0) FA_TRACE_EVENT(4 + t, its + j, 3);
 #pragma unroll
@@ -320,32 +316,32 @@ flash_fwd_kernel_sm100_p4(const __grid_constant__ CUtensorMap tmQ, const __grid_
                     } else {
 #pragma unroll
                         for (int q = 0; q < 4; ++q) {
-                            mbar_wait(&bar_p[4 * t + q], (its + j) & 1);
+                            mbar_wait(bar_p + 8 * (4 * t + q), (its + j) & 1);
                             tc_fence_after();
                             if (lane == 0) FA_TRACE_EVENT(4 + t, its + j, q);      // rows 4 / 5: MMA warp of tile 0 / 1
                             issue_pv(j, q);
                         }
                     }
-                    if (last && give && leader) mbar_arrive(&bar_tok[t ^ 1]);       // last block of the tile: no S follows
+                    if (last && give && leader) mbar_arrive(bar_tok + 8 * (t ^ 1));       // last block of the tile: no S follows
                     if (lane == 0) FA_TRACE_EVENT(4 + t, its + j, 4);
                     if (!last) {
                         issue_s(j + 1, give);
                     } else {
-                        commit(&bar_o_full[t]);
+                        commit(bar_o_full + 8 * (t));
                     }
                     if (lane == 0) FA_TRACE_EVENT(4 + t, its + j, 6);
-                    if (j + 2 == nbt) commit(&bar_q_empty[t]);                      // S_t of the last step issued
-                    commit(&bar_kv_empty[kv_slot(2 * j + 1)]);
-                    if (j + 1 < nbt) commit(&bar_kv_empty[kv_slot(2 * j + 2)]);
+                    if (j + 2 == nbt) commit(bar_q_empty + 8 * (t));                      // S_t of the last step issued
+                    commit(bar_kv_empty + 8 * (kv_slot(2 * j + 1)));
+                    if (j + 1 < nbt) commit(bar_kv_empty + 8 * (kv_slot(2 * j + 2)));
                     __syncwarp();
                 }
                 // K/V tiles only the other query tile needs (causal diagonal, ragged tails): let go of them in ring order,
                 // each only once it has landed — its slot's previous release is complete by then
                 for (int j = nbt; j < nbmax; ++j) {
                     wait_kv(2 * j);
-                    if (leader) mbar_arrive(&bar_kv_empty[kv_slot(2 * j)]);
+                    if (leader) mbar_arrive(bar_kv_empty + 8 * (kv_slot(2 * j)));
                     wait_kv(2 * j + 1);
-                    if (leader) mbar_arrive(&bar_kv_empty[kv_slot(2 * j + 1)]);
+                    if (leader) mbar_arrive(bar_kv_empty + 8 * (kv_slot(2 * j + 1)));
                     __syncwarp();
                 }
                 kv_i += 2 * nbmax;
@@ -355,126 +351,6 @@ flash_fwd_kernel_sm100_p4(const __grid_constant__ CUtensorMap tmQ, const __grid_
               }
               if (pass == 0) { pass_boundary(); if (pass_count(1) == 0) break; }
             }
-#else
-        } else if (warp == 16) {
-            // ===================== MMA issuer (warp-uniform walk, one elected lane issues) =====================
-            // ONE warp issues for both tiles, strictly alternating (tile 0: four P quarters + next S) (tile 1: ...).  That
-            // alternation is what keeps the two tiles half a period apart — one in its softmax while the other's MMAs run.
-            // Measured (profiles/r02_run5.log): one issuing warp per tile lets the tiles drift into the SAME phase (both
-            // softmax, then both MMA) and the period grows from ~2850 to ~3760 cycles (C2 1106 instead of 1322 TFLOP/s).
-            const bool leader = elect_one();
-            constexpr uint32_t idesc_s = make_idesc(kBf16, kBlockM, kBlockN, false, false);
-            constexpr uint32_t idesc_pv = make_idesc(kBf16, kBlockM, D, false, true);
-            const uint32_t tm = __shfl_sync(0xffffffffu, tmem_base, 0);
-            const uint32_t q_lo = __shfl_sync(0xffffffffu, desc_lo(smem_u32(sQ), 16), 0);
-            const uint32_t kv_lo = __shfl_sync(0xffffffffu, desc_lo(smem_u32(sKV), 16), 0);
-            const uint32_t v_lo = __shfl_sync(0xffffffffu, desc_lo(smem_u32(sKV), L::kSlab), 0);
-            constexpr uint32_t kTile16 = L::kTile >> 4;
-            int kv_i = 0;                 // ring index of K_0 of the current item
-            int it[2] = {0, 0};           // S_t / P_t steps so far (barrier parities)
-            int nitem[2] = {0, 0};        // items finished per tile slot (Q / O barrier parities)
-            for (int pass = 0; pass < 2; ++pass) {
-              const int cnt = pass_count(pass);
-              for (int idx = 0; idx < cnt; ++idx) {
-                const int n = pass_item(pass, idx);
-                const WorkItem w = decode_item(ts, n, p.h, p.is_causal != 0);
-                const ItemGeom g = item_geom(p, w);
-                const int nb0 = __shfl_sync(0xffffffffu, g.nblk[0], 0);
-                const int nb1 = __shfl_sync(0xffffffffu, g.nblk[1], 0);
-                const int nbmax = max(nb0, nb1);
-                if (__shfl_sync(0xffffffffu, (int)g.skip, 0) || nbmax == 0) continue;
-                auto kv_slot = [&](int i) { return (kv_i + i) % kStages; };
-                auto wait_kv = [&](int i) { mbar_wait(&bar_kv_full[kv_slot(i)], (((kv_i + i) / kStages) & 1)); };
-                auto commit = [&](uint64_t* bar) { if (leader) tc_commit(bar); };
-                auto issue_s = [&](int t, int j, int nbt) {  // S_t = Q_t K_j^T
-                    if (leader) {
-                        const uint32_t qa = q_lo + t * kTile16;
-                        const uint32_t ka = kv_lo + kv_slot(2 * j) * kTile16;
-#pragma unroll
-                        for (int kk = 0; kk < D / 16; ++kk) {
-                            const uint32_t off = ((kk >> 2) * L::kSlab + (kk & 3) * 32) >> 4;
-                            umma_ss(tm + kTmemS0 + t * 128, desc_make(qa + off, kDescHiK), desc_make(ka + off, kDescHiK),
-                                    idesc_s, kk > 0);
-                        }
-                        tc_commit(&bar_s_full[t]);
-                        if (j + 1 == nbt) tc_commit(&bar_q_empty[t]);   // Q_t may be overwritten by the next item
-                    }
-                };
-                // O_t += P_t[:, quarter q] V_j[quarter q]: key rows [16q, 16q+16) (P written by half 0) and
-                // [64+16q, 64+16q+16) (half 1); P quarter (hh, q) sits at S_t + 64 hh + 8 q
-                auto issue_pv = [&](int t, int j, int q) {
-                    if (leader) {
-                        const uint32_t va = v_lo + kv_slot(2 * j + 1) * kTile16;
-#pragma unroll
-                        for (int hh = 0; hh < 2; ++hh)
-                            umma_ts(tm + kTmemO0 + t * 128, tm + kTmemS0 + t * 128 + hh * 64 + q * 8,
-                                    desc_make(va + (hh * 4 + q) * (2048 >> 4), kDescHiK), idesc_pv, (j > 0 || q > 0 || hh > 0));
-                    }
-                };
-
-                wait_kv(0);
-                tc_fence_after();
-                if (nb0 > 0) { mbar_wait(&bar_q_full[0], nitem[0] & 1); issue_s(0, 0, nb0); }
-                if (nb1 > 0) { mbar_wait(&bar_q_full[1], nitem[1] & 1); issue_s(1, 0, nb1); }
-                commit(&bar_kv_empty[kv_slot(0)]);
-                bool v_ready = false;     // V_j was already seen full by the probe of the previous step
-                for (int j = 0; j < nbmax; ++j) {
-                    if (lane == 0) FA_TRACE_EVENT(4, it[0] + j, 0);      // trace: loop top / V_j there (rows 4: events 0, 1)
-                    if (!v_ready) wait_kv(2 * j + 1);  // V_j
-                    if (lane == 0) FA_TRACE_EVENT(4, it[0] + j, 1);
-                    v_ready = false;
-                    bool k_ready = false;
-#pragma unroll
-                    for (int t = 0; t < 2; ++t) {
-                        const int nbt = t == 0 ? nb0 : nb1;
-                        if (j < nbt) {
-                            if (j == 0) {   // O_t of the previous item must have been read out by its epilogue
-                                mbar_wait(&bar_o_empty[t], (nitem[t] & 1) ^ 1);
-                            }
-                            // The softmax warps hand P over quarter by quarter, in order.  When this warp gets here late (the
-                            // usual case: it was issuing the other tile's MMAs) all four quarters are there already, and four
-                            // waits on completed barriers (~90-200 cycles each with the sub-partition's softmax warps competing
-                            // for issue slots) let the tensor pipe run dry: probe the LAST quarter first.
-                            if (lane == 0) FA_TRACE_EVENT(4 + t, it[t] + j, 7);  // trace: about to probe
-                            if (mbar_test_wait(&bar_p[4 * t + 3], (it[t] + j) & 1)) {
-                                tc_fence_after();
-                                if (lane == 0) FA_TRACE_EVENT(4 + t, it[t] + j, 3);
-#pragma unroll
-                                for (int q = 0; q < 4; ++q) issue_pv(t, j, q);
-                            } else {
-#pragma unroll
-                                for (int q = 0; q < 4; ++q) {
-                                    mbar_wait(&bar_p[4 * t + q], (it[t] + j) & 1);
-                                    tc_fence_after();
-                                    if (lane == 0) FA_TRACE_EVENT(4 + t, it[t] + j, q);      // rows 4 / 5: MMA warp, tile 0 / 1
-                                    issue_pv(t, j, q);
-                                }
-                            }
-                            if (lane == 0) FA_TRACE_EVENT(4 + t, it[t] + j, 4);
-                            if (j + 1 < nbt) {
-                                if (!k_ready) { wait_kv(2 * j + 2); tc_fence_after(); k_ready = true; }
-                                if (lane == 0) FA_TRACE_EVENT(4 + t, it[t] + j, 5);
-                                // probe V_j+1 now, underneath the eight MMAs about to be queued, instead of after them
-                                if (t == 1 && j + 1 < nbmax)
-                                    v_ready = mbar_test_wait(&bar_kv_full[kv_slot(2 * j + 3)], (((kv_i + 2 * j + 3) / kStages) & 1));
-                                issue_s(t, j + 1, nbt);
-                            } else {
-                                commit(&bar_o_full[t]);
-                            }
-                            if (lane == 0) FA_TRACE_EVENT(4 + t, it[t] + j, 6);
-                        }
-                    }
-                    commit(&bar_kv_empty[kv_slot(2 * j + 1)]);
-                    if (j + 1 < nbmax) commit(&bar_kv_empty[kv_slot(2 * j + 2)]);
-                    __syncwarp();
-                }
-                kv_i += 2 * nbmax;
-                it[0] += nb0; it[1] += nb1;
-                nitem[0] += (nb0 > 0); nitem[1] += (nb1 > 0);
-              }
-              if (pass == 0) { pass_boundary(); if (pass_count(1) == 0) break; }
-            }
-#endif
         } else {
             // ===================== store warp(s): TMA store of the staged O tiles =====================
             // The softmax warpgroups only write the staging tile and arrive on a named barrier; issuing the bulk store and
@@ -482,7 +358,6 @@ flash_fwd_kernel_sm100_p4(const __grid_constant__ CUtensorMap tmQ, const __grid_
             // thread did it, its whole warp sat in that wait and — every P quarter needs all eight warps of a tile — held
             // up the tile's first key steps of the next item (clock64: the next item's first S was picked up ~1200 cycles
             // after the epilogue had finished, profiles/r02_run3.log).
-#if FA_P4_MMA2
             // One warp serves both tiles: whoever holds the staging lock describes the tile in store_desc and arrives on
             // barrier 11; this warp only has to know HOW MANY whole tiles the CTA's items produce in this pass.
             for (int pass = 0; pass < 2; ++pass) {
@@ -503,12 +378,12 @@ flash_fwd_kernel_sm100_p4(const __grid_constant__ CUtensorMap tmQ, const __grid_
               for (int i = 0; i < n_store; ++i) {
                 named_bar_sync(11, 2 * kBlockM + 32);              // staging tile written and fenced by a tile's 256 threads
                 if (lane == 0) {
-                    volatile int* sd = store_desc;
-                    const int bidh = sd[0], row0 = sd[1], tb = sd[2], n = sd[3], pzi = sd[4];
-                    if (poison[pzi]) {                             // some row of this tile overflowed its speculative step: redo the item
-                        poison[pzi] = 0;
-                        const int k2 = atomicAdd(retry_count, 1);
-                        if (k2 < kMaxRetry) retry_list[k2] = n;
+                    const int bidh = lds32(store_desc), row0 = lds32(store_desc + 4), tb = lds32(store_desc + 8);
+                    const int n = lds32(store_desc + 12), pzi = lds32(store_desc + 16);
+                    if (lds32(poison + 4 * pzi)) {                 // some row of this tile overflowed its speculative step: redo the item
+                        sts32(poison + 4 * pzi, 0);
+                        const int k2 = atoms_add(retry_count, 1);
+                        if (k2 < kMaxRetry) sts32(retry_list + 4 * k2, n);
                     }
 #pragma unroll
                     for (int sl = 0; sl < kSlabs; ++sl)
@@ -516,7 +391,7 @@ flash_fwd_kernel_sm100_p4(const __grid_constant__ CUtensorMap tmQ, const __grid_
                     tma_store_commit();
                     tma_store_wait_read<0>();                      // staging tile has been read; global writes complete later
                     __threadfence_block();
-                    atomicExch(stage_lock, 0);                     // the other tile's epilogue (or this tile's next one) may take it
+                    atoms_exch(stage_lock, 0);                     // the other tile's epilogue (or this tile's next one) may take it
                 }
                 __syncwarp();
               }
@@ -524,44 +399,6 @@ flash_fwd_kernel_sm100_p4(const __grid_constant__ CUtensorMap tmQ, const __grid_
               __syncwarp();
               if (pass == 0) { pass_boundary(); if (pass_count(1) == 0) break; }
             }
-#else
-            const int t = warp - kStoreWarp0;
-            int nit = 0;                                           // items in which this tile had keys (= the softmax warps' nitem)
-            for (int pass = 0; pass < 2; ++pass) {
-              const int cnt = pass_count(pass);
-              for (int idx = 0; idx < cnt; ++idx) {
-                const int n = pass_item(pass, idx);
-                const WorkItem w = decode_item(ts, n, p.h, p.is_causal != 0);
-                const ItemGeom g = item_geom(p, w);
-                if (g.skip) continue;
-                const int mt = g.m0 + t * kBlockM;
-                if (mt >= g.sq_b || g.nblk[t] == 0) continue;
-                const int par = nit & 1;
-                ++nit;
-                const bool whole_tile = (mt + kBlockM <= g.sq_b) || (p.cu_q == nullptr);
-                if (!whole_tile) continue;                         // ragged varlen tail: stored by the softmax threads themselves
-                named_bar_sync(11 + t, 2 * kBlockM + 32);          // staging tile written and fenced by the tile's 256 threads
-                if (lane == 0) {
-                    if (poison[2 * t + par]) {                     // some row of this tile overflowed its speculative step: redo the item
-                        poison[2 * t + par] = 0;
-                        const int k2 = atomicAdd(retry_count, 1);
-                        if (k2 < kMaxRetry) retry_list[k2] = n;
-                    }
-#pragma unroll
-                    for (int sl = 0; sl < kSlabs; ++sl)
-                        tma_store_4d(&tmO, sStage + sl * L::kSlab, sl * 64, w.bidh, g.q_row0 + mt, g.tma_b);
-                    tma_store_commit();
-                    tma_store_wait_read<0>();                      // staging tile has been read; global writes complete later
-                    __threadfence_block();
-                    atomicExch(stage_lock, 0);                     // the other tile's epilogue (or this tile's next one) may take it
-                }
-                __syncwarp();
-              }
-              if (lane == 0) tma_store_wait<0>();                  // all bulk stores have landed before a retry rewrites the tile / the CTA retires
-              __syncwarp();
-              if (pass == 0) { pass_boundary(); if (pass_count(1) == 0) break; }
-            }
-#endif
         }
     } else {
         // ========== softmax warpgroups: warpgroup 2t+hh owns columns [64hh, 64hh+64) of tile slot t, one thread per row ==========
@@ -659,7 +496,7 @@ flash_fwd_kernel_sm100_p4(const __grid_constant__ CUtensorMap tmQ, const __grid_
             tmem_wait_st();
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&bar_p[4 * t + q]);
+            if (lane == 0) mbar_arrive(bar_p + 8 * (4 * t + q));
             if (lane == 0) FA_TRACE_EVENT(trole, tr_step, 2 + q);
         };
 
@@ -678,7 +515,7 @@ flash_fwd_kernel_sm100_p4(const __grid_constant__ CUtensorMap tmQ, const __grid_
                 if (g.skip) continue;
                 const int mt = g.m0 + t * kBlockM;
                 if (mt >= g.sq_b) continue;                  // this slot has no rows in this item (nblk[t] == 0 too)
-                n_t = g.nblk[t];
+                n_t = t == 0 ? g.nblk[0] : g.nblk[1];            // (a run-time index would put the struct into local memory)
                 const int row = mt + r_in_tile;
                 if (n_t == 0) {
                     // rows exist but see no key: O = 0, LSE = 0 (each half clears its D/2 columns)
@@ -703,7 +540,7 @@ flash_fwd_kernel_sm100_p4(const __grid_constant__ CUtensorMap tmQ, const __grid_
             float neg = 0.f, l_run = 0.f;
             bool has_ref = false;
             hs16 = 0;
-            int* pz = &poison[2 * t + (nitem & 1)];
+            const uint32_t pz = poison + 4 * (2 * t + (nitem & 1));
 
             // ------------------------------------------------------------------------------------------------------
             // exact step: row max first (pass 1), then the exponentials.  Every step of a retried item, and the first
@@ -715,7 +552,7 @@ flash_fwd_kernel_sm100_p4(const __grid_constant__ CUtensorMap tmQ, const __grid_
                 tr_step = its + j;
                 const int lim = lim0 - j * kBlockN;            // last visible column of this thread's 64 (may be < 0 or >= 64)
                 if (j == 0 && (tid & 31) == 0) FA_TRACE_EVENT(trole, its, 7);   // first step of an item: about to wait for its S
-                mbar_wait(&bar_s_full[t], (its + j) & 1);
+                mbar_wait(bar_s_full + 8 * (t), (its + j) & 1);
                 tc_fence_after();
                 if ((tid & 31) == 0) FA_TRACE_EVENT(trole, its + j, 0);
 
@@ -840,7 +677,7 @@ flash_fwd_kernel_sm100_p4(const __grid_constant__ CUtensorMap tmQ, const __grid_
                 using spec = std::true_type;
                 tr_step = its + j;
                 const int lim = lim0 - j * kBlockN;
-                mbar_wait(&bar_s_full[t], (its + j) & 1);
+                mbar_wait(bar_s_full + 8 * (t), (its + j) & 1);
                 tc_fence_after();
                 if ((tid & 31) == 0) FA_TRACE_EVENT(trole, its + j, 0);
                 float sa[16], sb[16];
@@ -907,7 +744,7 @@ flash_fwd_kernel_sm100_p4(const __grid_constant__ CUtensorMap tmQ, const __grid_
                 const float hs = sum.x + sum.y;
                 // overflow (also inf / NaN), or no reference yet (only an exact step can establish one; with prefix masks a row
                 // that saw no key in the first tile sees none at all and never gets here with more than one key step)
-                if (!(hs <= kOverflowAt) || (!has_ref && hs != 0.f)) *reinterpret_cast<volatile int*>(pz) = 1;
+                if (!(hs <= kOverflowAt) || (!has_ref && hs != 0.f)) sts32(pz, 1);
                 l_run += hs;
             };
             for (int j = 0; j < n_t; ++j) {
@@ -939,21 +776,21 @@ flash_fwd_kernel_sm100_p4(const __grid_constant__ CUtensorMap tmQ, const __grid_
             const bool row_empty = !has_ref || !(l_tot > 0.f);   // no visible key: O = 0, LSE = 0
             const float inv_l = row_empty ? 0.f : (1.f / l_tot);
             if ((tid & 31) == 0) FA_TRACE_EVENT(erole, nitem, 2);
-            mbar_wait(&bar_o_full[t], nitem & 1);
+            mbar_wait(bar_o_full + 8 * (t), nitem & 1);
             tc_fence_after();
             if ((tid & 31) == 0) FA_TRACE_EVENT(erole, nitem, 1);
             if (hh == 0 && wq == 0) {    // take the staging tile (the other tile's store may still be reading it); the whole warp
                 int got;                 // spins together: bar.sync below is warp-aligned
                 do {
                     got = 0;
-                    if (lane == 0) got = (atomicCAS(stage_lock, 0, 1) == 0);
+                    if (lane == 0) got = (atoms_cas(stage_lock, 0, 1) == 0);
                     got = __shfl_sync(0xffffffffu, got, 0);
                     if (!got) __nanosleep(32);
                 } while (!got);
             }
             named_bar_sync(tile_bar, 2 * kBlockM);
             if ((tid & 31) == 0) FA_TRACE_EVENT(erole, nitem, 3);
-            const uint32_t stage = smem_u32(sStage);
+            const uint32_t stage = sStage;
 #pragma unroll
             for (int c = 0; c < kHalfD / 32; ++c) {
                 uint32_t o[32];
@@ -962,7 +799,7 @@ flash_fwd_kernel_sm100_p4(const __grid_constant__ CUtensorMap tmQ, const __grid_
                 if (c == kHalfD / 32 - 1) {     // O_t is in registers: the next item's first P V may overwrite it
                     tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(&bar_o_empty[t]);
+                    if (lane == 0) mbar_arrive(bar_o_empty + 8 * (t));
                     if (lane == 0) FA_TRACE_EVENT(erole, nitem, 4);
                 }
 #pragma unroll
@@ -978,23 +815,17 @@ flash_fwd_kernel_sm100_p4(const __grid_constant__ CUtensorMap tmQ, const __grid_
             }
             if (hh == 0 && row < g.sq_b) lse_row[row] = row_empty ? 0.f : fmaf(-neg, 0.6931471805599453f, logf(l_tot));   // m_ref / sqrt(d) + ln l
             if ((tid & 31) == 0) FA_TRACE_EVENT(erole, nitem, 5);
-#if FA_P4_MMA2
             if (hh == 0 && r_in_tile == 0) {                   // tell the store warp what the staging tile holds
-                volatile int* sd = store_desc;
-                sd[0] = w.bidh; sd[1] = g.q_row0 + mt; sd[2] = g.tma_b; sd[3] = n_again; sd[4] = 2 * t + (nitem & 1);
+                sts32(store_desc, w.bidh); sts32(store_desc + 4, g.q_row0 + mt); sts32(store_desc + 8, g.tma_b);
+                sts32(store_desc + 12, n_again); sts32(store_desc + 16, 2 * t + (nitem & 1));
                 __threadfence_block();
             }
-#endif
             fence_proxy_async_smem();                          // generic-proxy writes -> visible to the TMA engine
             const bool whole_tile = (mt + kBlockM <= g.sq_b) || (p.cu_q == nullptr);   // dense: TMA clips rows >= seqlen_q itself
             if (whole_tile) {
                 // hand the tile to the store warp and move on: it checks the overflow flag, issues the bulk store and
                 // releases the staging tile once the engine has read it
-#if FA_P4_MMA2
                 named_bar_arrive(11, 2 * kBlockM + 32);
-#else
-                named_bar_arrive(11 + t, 2 * kBlockM + 32);
-#endif
             } else {
                 // ragged varlen tail: a TMA box would spill into the next sequence -> predicated coalesced stores
                 constexpr int kChunksPerRow = D / 8;
@@ -1008,12 +839,12 @@ flash_fwd_kernel_sm100_p4(const __grid_constant__ CUtensorMap tmQ, const __grid_
                 }
                 named_bar_sync(tile_bar, 2 * kBlockM);
                 if (hh == 0 && r_in_tile == 0) {
-                    if (*reinterpret_cast<volatile int*>(pz)) {       // (the store warp does this for whole tiles)
-                        *reinterpret_cast<volatile int*>(pz) = 0;
-                        const int k2 = atomicAdd(retry_count, 1);
-                        if (k2 < kMaxRetry) retry_list[k2] = n;
+                    if (lds32(pz)) {                                  // (the store warp does this for whole tiles)
+                        sts32(pz, 0);
+                        const int k2 = atoms_add(retry_count, 1);
+                        if (k2 < kMaxRetry) sts32(retry_list + 4 * k2, n);
                     }
-                    atomicExch(stage_lock, 0);
+                    atoms_exch(stage_lock, 0);
                 }
                 __syncwarp();
             }

@@ -17,6 +17,10 @@ namespace fa100 {
 // address helpers
 // ------------------------------------------------------------------------------------------------
 FA_DEVICE uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+// Every helper below that names a shared-memory location takes either a generic pointer or a 32-bit address in the shared
+// window.  Kernels that keep only 32-bit addresses never hold the 64-bit generic base pointer: in the forward kernel it was
+// the one value ptxas spilled, and with all of L1 configured as shared memory every reload was an L2 round trip.
+FA_DEVICE uint32_t smem_u32(uint32_t shared_window_address) { return shared_window_address; }
 
 FA_DEVICE bool elect_one() {
     uint32_t pred = 0;
@@ -33,20 +37,20 @@ FA_DEVICE bool elect_one() {
 // ------------------------------------------------------------------------------------------------
 // mbarrier
 // ------------------------------------------------------------------------------------------------
-FA_DEVICE void mbar_init(uint64_t* bar, uint32_t count) {
+template <class B> FA_DEVICE void mbar_init(B bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
 }
 FA_DEVICE void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 FA_DEVICE void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-FA_DEVICE void mbar_arrive(uint64_t* bar) {
+template <class B> FA_DEVICE void mbar_arrive(B bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-FA_DEVICE void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+template <class B> FA_DEVICE void mbar_arrive_expect_tx(B bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
                  : "memory");
 }
-FA_DEVICE bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+template <class B> FA_DEVICE bool mbar_try_wait(B bar, uint32_t parity) {
     uint32_t ok;
     asm volatile(
         "{\n\t"
@@ -60,7 +64,7 @@ FA_DEVICE bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
     return ok != 0;
 }
 // Non-blocking probe of a phase (test_wait never suspends the thread).
-FA_DEVICE bool mbar_test_wait(uint64_t* bar, uint32_t parity) {
+template <class B> FA_DEVICE bool mbar_test_wait(B bar, uint32_t parity) {
     uint32_t ok;
     asm volatile(
         "{\n\t"
@@ -76,7 +80,7 @@ FA_DEVICE bool mbar_test_wait(uint64_t* bar, uint32_t parity) {
 // Blocking wait on phase parity.  try_wait is a hardware-suspended wait with a time limit, so the loop
 // spins at most a few times.  With FA_HANG_GUARD the wait traps after ~2^28 polls instead of hanging the
 // GPU box (used in bring-up builds).
-FA_DEVICE void mbar_wait(uint64_t* bar, uint32_t parity) {
+template <class B> FA_DEVICE void mbar_wait(B bar, uint32_t parity) {
 #ifdef FA_HANG_GUARD
     uint32_t spins = 0;
     while (!mbar_try_wait(bar, parity)) {
@@ -106,7 +110,7 @@ template <int N> FA_DEVICE void setmaxnreg_dec() { asm volatile("setmaxnreg.dec.
 FA_DEVICE void tma_prefetch_desc(const CUtensorMap* m) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
 }
-FA_DEVICE void tma_load_4d(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2, int c3) {
+template <class D, class B> FA_DEVICE void tma_load_4d(D smem_dst, const CUtensorMap* m, B bar, int c0, int c1, int c2, int c3) {
     asm volatile(
         "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes"
         " [%0], [%1, {%3, %4, %5, %6}], [%2];"
@@ -114,7 +118,7 @@ FA_DEVICE void tma_load_4d(void* smem_dst, const CUtensorMap* m, uint64_t* bar, 
         "r"(c2), "r"(c3)
         : "memory");
 }
-FA_DEVICE void tma_load_4d_hint(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2,
+template <class D, class B> FA_DEVICE void tma_load_4d_hint(D smem_dst, const CUtensorMap* m, B bar, int c0, int c1, int c2,
                                 int c3, uint64_t policy) {
     asm volatile(
         "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.L2::cache_hint"
@@ -123,7 +127,7 @@ FA_DEVICE void tma_load_4d_hint(void* smem_dst, const CUtensorMap* m, uint64_t* 
         "r"(c2), "r"(c3), "l"(policy)
         : "memory");
 }
-FA_DEVICE void tma_store_4d(const CUtensorMap* m, const void* smem_src, int c0, int c1, int c2, int c3) {
+template <class S> FA_DEVICE void tma_store_4d(const CUtensorMap* m, S smem_src, int c0, int c1, int c2, int c3) {
     asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
                  ::"l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
                  : "memory");
@@ -142,7 +146,7 @@ constexpr uint64_t kPolicyEvictNormal = 0x1000000000000000ull;
 // ------------------------------------------------------------------------------------------------
 // tcgen05: TMEM allocation
 // ------------------------------------------------------------------------------------------------
-template <int NCOLS> FA_DEVICE void tmem_alloc(uint32_t* smem_result) {  // whole warp, .sync.aligned
+template <int NCOLS, class R> FA_DEVICE void tmem_alloc(R smem_result) {  // whole warp, .sync.aligned
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_result)),
                  "n"(NCOLS)
                  : "memory");
@@ -159,7 +163,7 @@ FA_DEVICE void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::
 
 // tcgen05.commit: arrive (count 1) on an mbarrier once all previously issued tcgen05.mma of this thread
 // have completed.  Implies tcgen05.fence::before_thread_sync.
-FA_DEVICE void tc_commit(uint64_t* bar) {
+template <class B> FA_DEVICE void tc_commit(B bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                  : "memory");
 }
@@ -287,6 +291,11 @@ FA_DEVICE uint4 lds128u(uint32_t saddr) {
 FA_DEVICE void sts128u(uint32_t saddr, uint4 v) {
     asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
+FA_DEVICE int lds32(uint32_t saddr) { int v; asm volatile("ld.volatile.shared.b32 %0, [%1];" : "=r"(v) : "r"(saddr) : "memory"); return v; }
+FA_DEVICE void sts32(uint32_t saddr, int v) { asm volatile("st.volatile.shared.b32 [%0], %1;" ::"r"(saddr), "r"(v) : "memory"); }
+FA_DEVICE int atoms_add(uint32_t saddr, int v) { int o; asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(o) : "r"(saddr), "r"(v) : "memory"); return o; }
+FA_DEVICE int atoms_cas(uint32_t saddr, int cmp, int v) { int o; asm volatile("atom.shared.cas.b32 %0, [%1], %2, %3;" : "=r"(o) : "r"(saddr), "r"(cmp), "r"(v) : "memory"); return o; }
+FA_DEVICE int atoms_exch(uint32_t saddr, int v) { int o; asm volatile("atom.shared.exch.b32 %0, [%1], %2;" : "=r"(o) : "r"(saddr), "r"(v) : "memory"); return o; }
 FA_DEVICE void sts32f(uint32_t saddr, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(saddr), "f"(v) : "memory"); }
 
 // ------------------------------------------------------------------------------------------------
