@@ -758,7 +758,12 @@ flash_fwd_kernel_sm100_p4(const __grid_constant__ CUtensorMap tmQ, const __grid_
             }
             its += n_t;
 
-            // ---- epilogue: O_t / l -> 16 bit -> staging tile (128B-swizzled, the TMA layout) -> TMA store by warp 18 + t ----
+            // ---- epilogue: O_t / l -> 16 bit -> staging tile (128B-swizzled, the TMA layout) -> TMA store by warp 19 ----
+            // Measured alternatives (profiles/r02_run24.log, r02_run25.log): storing O straight from registers with 32-byte
+            // global stores (no staging tile, no lock, no proxy fence) — the scattered stores back up in the LSU for ~2000
+            // cycles per tile: neutral at seqlen >= 4096, 2.5-4 % slower at seqlen 512-1024; looking up the NEXT item before
+            // this epilogue (the work-list decode is a ~1000-cycle dependent integer chain per item) — +0.3-0.9 % at head_dim
+            // 128, -0.7 ... -2.7 % at head_dim 64 (two more values spilled), not kept.
             if ((tid & 31) == 0) FA_TRACE_EVENT(erole, nitem, 0);     // rows 6 / 7: epilogue of item `nitem` (0 start, 1 O full, 2 l exchanged,
             int n_again = n;                                           //   3 staging tile free, 4 O in registers, 5 staged, 6 handed over)
             asm volatile("" : "+r"(n_again));                  // opaque copy: keeps the geometry from living across the key loop
