@@ -2,7 +2,7 @@
 # Evidence for profiles/ (one B200): ncu launch list of the bench command + full captures of every kernel, the
 # benchmark.sh-grid sweep (fp16 + bf16, head_dim 64 / 128), the reference's full acceptance matrix for this module and for
 # the reference's own kernels rebuilt for sm_100a.
-O=gpurun_out/evidence; mkdir -p $O
+O=gpurun_out/evidence2; mkdir -p $O
 L=$O/evidence.log; : > $L
 echo "== launch list of the bench command (shares, cold-cache)" >> $L
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/launches_bench.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-e2e > $O/bench_under_ncu.json 2>> $L
