@@ -28,6 +28,18 @@
 #include "flash_bwd_params.h"
 #include "sm100_ptx.cuh"
 
+#ifndef FA_FUSED_D64_DEFAULT
+#define FA_FUSED_D64_DEFAULT 1   // head_dim 64 takes the fused backward too (+17-22 % over the two deterministic kernels, profiles/r02_run27.log); FA_B200_BWD_D64=det / fused override
+#endif
+#ifndef FA_FUSED_RED_COLS64
+#define FA_FUSED_RED_COLS64 16  // the same at head_dim 64 (a red.global instruction only carries 16 lanes x 4 bytes there)
+#endif
+#ifndef FA_FUSED_STAGES64
+#define FA_FUSED_STAGES64 6     // Q / dO ring depth at head_dim 64 (shared memory is plentiful there)
+#endif
+#ifndef FA_FUSED_EMU64
+#define FA_FUSED_EMU64 0        // head_dim 64: column pairs out of every 8 whose 2^x goes through the FMA-pipe polynomial
+#endif
 #ifndef FA_FUSED_RED_COLS
 #define FA_FUSED_RED_COLS 16   // query rows per step whose dQ leaves through red.global (the rest: one bulk reduction)
 #endif
@@ -685,7 +697,7 @@ template <int D> struct FzSmem {
     static constexpr int kTile = kBM * D * 2;
     static constexpr int kSubSlab = kSubQ * 128;
     static constexpr int kSub = kSubQ * D * 2;
-    static constexpr int kStages = 3;                               // one less than the plain kernel: pays for the dQ staging tile
+    static constexpr int kStages = D == 64 ? FA_FUSED_STAGES64 : 3;                 // D = 128: one less than the plain kernel (pays for the dQ staging tile)
     static constexpr int kOffK = 0;
     static constexpr int kOffV = kTile;
     static constexpr int kOffQdO = 2 * kTile;
@@ -695,7 +707,7 @@ template <int D> struct FzSmem {
     static constexpr int kOffBar = kOffDQ + kSubQ * D * 4;
     static constexpr int kBytes = kOffBar + 256 + 1024;
 };
-static_assert(FzSmem<128>::kBytes <= 232448, "fused backward: shared memory budget");
+static_assert(FzSmem<128>::kBytes <= 232448 && FzSmem<64>::kBytes <= 232448, "fused backward: shared memory budget");
 namespace fzt { constexpr uint32_t kSt = 0, kDPt = 64, kPt = 128, kDSt = 160, kDQt = 192, kDV = 256, kDK = 384; }
 
 // kAcc16 (FA_B200_BWD_ACC=16, experiment): the partial dQ tiles are reduced in fp16 instead of fp32 (half the L2 reduction
@@ -765,6 +777,9 @@ flash_bwd_dk_dv_kernel_sm100_fused(const __grid_constant__ CUtensorMap tmQ, cons
 
     if (warp == 8) {
         if (lane == 0) {
+#ifdef FA_HANG_GUARD
+            g_hang_info[6] = smem_u32(bars); g_hang_info[7] = (uint32_t)total;
+#endif
             mbar_init(bar_kv, 1);
             for (int i = 0; i < L::kStages; ++i) { mbar_init(&bar_qdo_full[i], 1); mbar_init(&bar_qdo_empty[i], 1); }
             mbar_init(bar_s_full, 1); mbar_init(bar_s_empty, 256);
@@ -792,15 +807,19 @@ flash_bwd_dk_dv_kernel_sm100_fused(const __grid_constant__ CUtensorMap tmQ, cons
         // accumulator is head-major ([b][h][sq_pad][d]) so the 64 q rows of a step are contiguous in global memory.
         // (Tried first, see DESIGN.md: per-thread red.global.add.f32, per-row 512-byte bulk reductions, and draining from
         //  the elementwise warpgroups — all slower.)
+        // head_dim 64: dQ^T is an M = 64 accumulator — row d sits on lane 16 (d / 16) ... of TMEM, i.e. on lanes 0-15 of
+        // every warp's 32-lane quarter; the upper half of each drain warp holds nothing and only keeps the barriers company.
         setmaxnreg_dec<40>();
         const int tw = tid & 127;
-        const int r = ((warp & 3) << 5) | lane;
+        constexpr bool kM64 = (D == 64);
+        const bool dvalid = !kM64 || lane < 16;
+        const int r = kM64 ? (((warp & 3) << 4) | (lane & 15)) : (((warp & 3) << 5) | lane);
         const uint32_t tDQt = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + fzt::kDQt;
         const uint32_t sDQr = smem_u32(smem + L::kOffDQ) + r * (kAcc16 ? 2 : 4);
         // The bulk-reduction engine of an SM moves ~15 B/clk: 32 KB of fp32 per step would take longer than the step's MMAs.
         // The first kRedCols query rows of every step therefore leave through per-thread red.global.add.f32 straight from
         // registers (a different path: LSU -> L2), the rest through the staging tile and ONE bulk reduction.
-        constexpr int kRedCols = kAcc16 ? 0 : FA_FUSED_RED_COLS;
+        constexpr int kRedCols = kAcc16 ? 0 : (kM64 ? FA_FUSED_RED_COLS64 : FA_FUSED_RED_COLS);
         constexpr int kBulkRows = kSubQ - kRedCols;
         for (int s = 0; s < total; ++s) {
             const int hq = bidh_k * p.hratio + s / steps_per_head;
@@ -818,22 +837,26 @@ flash_bwd_dk_dv_kernel_sm100_fused(const __grid_constant__ CUtensorMap tmQ, cons
                 }
                 if (qt * 16 < kRedCols) {
                     float* dst = p.dqacc + eoff + (qt * 16) * D + r;
+                    if (dvalid) {
 #pragma unroll
-                    for (int c = 0; c < 16; ++c)
-                        asm volatile("red.global.add.f32 [%0], %1;" ::"l"(dst + c * D), "f"(__uint_as_float(v[c])) : "memory");
+                        for (int c = 0; c < 16; ++c)
+                            asm volatile("red.global.add.f32 [%0], %1;" ::"l"(dst + c * D), "f"(__uint_as_float(v[c])) : "memory");
+                    }
                 } else {
                     if (qt * 16 == kRedCols) {
                         if (tw == 0) tma_store_wait_read<0>();   // the previous step's bulk reduction has read the staging tile
                         named_bar_sync(2, 128);
                     }
+                    if (dvalid) {
 #pragma unroll
-                    for (int c = 0; c < 16; ++c) {
-                        if constexpr (kAcc16) {
-                            uint16_t hv;
-                            asm("cvt.rn.f16.f32 %0, %1;" : "=h"(hv) : "f"(__uint_as_float(v[c])));
-                            asm volatile("st.shared.b16 [%0], %1;" ::"r"(sDQr + (qt * 16 - kRedCols + c) * (D * 2)), "h"(hv) : "memory");
-                        } else {
-                            asm volatile("st.shared.b32 [%0], %1;" ::"r"(sDQr + (qt * 16 - kRedCols + c) * (D * 4)), "r"(v[c]) : "memory");
+                        for (int c = 0; c < 16; ++c) {
+                            if constexpr (kAcc16) {
+                                uint16_t hv;
+                                asm("cvt.rn.f16.f32 %0, %1;" : "=h"(hv) : "f"(__uint_as_float(v[c])));
+                                asm volatile("st.shared.b16 [%0], %1;" ::"r"(sDQr + (qt * 16 - kRedCols + c) * (D * 2)), "h"(hv) : "memory");
+                            } else {
+                                asm volatile("st.shared.b32 [%0], %1;" ::"r"(sDQr + (qt * 16 - kRedCols + c) * (D * 4)), "r"(v[c]) : "memory");
+                            }
                         }
                     }
                 }
@@ -1021,7 +1044,7 @@ flash_bwd_dk_dv_kernel_sm100_fused(const __grid_constant__ CUtensorMap tmQ, cons
                 const float2 nl = (i & 1) ? make_float2(nl4[i >> 1].z, nl4[i >> 1].w) : make_float2(nl4[i >> 1].x, nl4[i >> 1].y);
                 const float2 dd = (i & 1) ? make_float2(dd4[i >> 1].z, dd4[i >> 1].w) : make_float2(dd4[i >> 1].x, dd4[i >> 1].y);
                 const float2 x = __ffma2_rn(make_float2(s[2 * i], s[2 * i + 1]), c2v, nl);
-                float2 pr = make_float2(fast_exp2(x.x), fast_exp2(x.y));
+                float2 pr = (D == 64 && (i & 7) < FA_FUSED_EMU64) ? exp2_poly_pair(x) : make_float2(fast_exp2(x.x), fast_exp2(x.y));
                 if (need_mask) {
                     if (2 * i < cmin) pr.x = 0.f;
                     if (2 * i + 1 < cmin) pr.y = 0.f;
@@ -1102,13 +1125,13 @@ flash_bwd_dk_dv_kernel_sm100_fused(const __grid_constant__ CUtensorMap tmQ, cons
 }
 
 
-// dQ[b, i, h, :] = round16(scale * acc[b, h, i, :]): 16 lanes x 8 elements per row, 16 rows per block, HBM-bound
-template <bool kBf16, bool kAcc16>
+// dQ[b, i, h, :] = round16(scale * acc[b, h, i, :]): D / 8 lanes x 8 elements per row, 2048 / D rows per block, HBM-bound
+template <int D, bool kBf16, bool kAcc16>
 __global__ void __launch_bounds__(256)
 flash_bwd_dq_kernel_sm100_convert(const BwdParams p) {
-    constexpr int D = 128;
+    constexpr int kLanes = D / 8;
     const int bidb = blockIdx.z, bidh = blockIdx.y;
-    const int i = blockIdx.x * 16 + (threadIdx.x >> 4), ch = threadIdx.x & 15;
+    const int i = blockIdx.x * (256 / kLanes) + (threadIdx.x / kLanes), ch = threadIdx.x % kLanes;
     int q_row0 = 0, sq_b = p.sq;
     if (p.cu_q) { q_row0 = p.cu_q[bidb]; sq_b = min(p.cu_q[bidb + 1] - q_row0, p.sq); }
     if (i >= sq_b) return;
@@ -1170,9 +1193,16 @@ bool bwd_fused_enabled() {
     if (v < 0) { const char* e = getenv("FA_B200_BWD"); v = (!e || e[0] == 'f') ? 1 : 0; }   // default; "det" / "rows" select the others
     return v == 1;
 }
+// head_dim 64 (FA_B200_BWD_D64=det selects the two deterministic kernels instead): the same fused kernel with an M = 64 dQ^T
+static bool bwd_fused_d64_enabled() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("FA_B200_BWD_D64"); v = e ? (e[0] == 'f' ? 1 : 0) : FA_FUSED_D64_DEFAULT; }
+    return v == 1;
+}
+static bool bwd_fused_for(long long d) { return bwd_fused_enabled() && (d == 128 || (d == 64 && bwd_fused_d64_enabled())); }
 long long bwd_fused_workspace_bytes(long long b, long long sq_max, long long h, long long d) {
     // fp32 accumulator [b][h][sq_pad][d], sq_pad = sq_max rounded up to the 64-row step of the kernel
-    return (bwd_fused_enabled() && d == 128) ? b * h * ((sq_max + 63) / 64 * 64) * d * 4 : 0;
+    return bwd_fused_for(d) ? b * h * ((sq_max + 63) / 64 * 64) * d * 4 : 0;
 }
 
 static bool bwd_acc16() {
@@ -1181,10 +1211,9 @@ static bool bwd_acc16() {
     return v == 1;
 }
 
-template <bool kBf16, bool kAcc16>
+template <int D, bool kBf16, bool kAcc16>
 static int launch_fused(const BwdParams& kp, const CUtensorMap& tq64, const CUtensorMap& tdo64, const CUtensorMap& tk,
                         const CUtensorMap& tv, cudaStream_t stream) {
-    constexpr int D = 128;
     auto kern = flash_bwd_dk_dv_kernel_sm100_fused<D, kBf16, kAcc16>;
     const DeviceInfo* di = nullptr;
     int rc = current_device_info(&di);
@@ -1196,8 +1225,9 @@ static int launch_fused(const BwdParams& kp, const CUtensorMap& tq64, const CUte
     kern<<<g, 512, FzSmem<D>::kBytes, stream>>>(tq64, tdo64, tk, tv, kp);
     FA_CUDA_CHECK(cudaGetLastError());
     count_launch();
-    dim3 gc((kp.sq + 15) / 16, kp.h, kp.b);
-    flash_bwd_dq_kernel_sm100_convert<kBf16, kAcc16><<<gc, 256, 0, stream>>>(kp);
+    constexpr int kRowsPerBlock = 256 / (D / 8);
+    dim3 gc((kp.sq + kRowsPerBlock - 1) / kRowsPerBlock, kp.h, kp.b);
+    flash_bwd_dq_kernel_sm100_convert<D, kBf16, kAcc16><<<gc, 256, 0, stream>>>(kp);
     FA_CUDA_CHECK(cudaGetLastError());
     count_launch();
     return FA_OK;
@@ -1228,9 +1258,11 @@ int launch_bwd_tc_sm100(const BwdParams& kp, bool bf16, cudaStream_t stream) {
         if ((rc = encode_tmap_4d(&tk, kp.k, bf16, dims, str, box128)) != FA_OK) return rc;
         if ((rc = encode_tmap_4d(&tv, kp.v, bf16, dims, str, box128)) != FA_OK) return rc;
     }
-    if (kp.d == 128 && bwd_fused_enabled() && kp.dqacc != nullptr)
-        return bwd_acc16() ? (bf16 ? launch_fused<true, true>(kp, tq64, tdo64, tk, tv, stream) : launch_fused<false, true>(kp, tq64, tdo64, tk, tv, stream))
-                           : (bf16 ? launch_fused<true, false>(kp, tq64, tdo64, tk, tv, stream) : launch_fused<false, false>(kp, tq64, tdo64, tk, tv, stream));
+    if (kp.d == 128 && bwd_fused_for(128) && kp.dqacc != nullptr)
+        return bwd_acc16() ? (bf16 ? launch_fused<128, true, true>(kp, tq64, tdo64, tk, tv, stream) : launch_fused<128, false, true>(kp, tq64, tdo64, tk, tv, stream))
+                           : (bf16 ? launch_fused<128, true, false>(kp, tq64, tdo64, tk, tv, stream) : launch_fused<128, false, false>(kp, tq64, tdo64, tk, tv, stream));
+    if (kp.d == 64 && bwd_fused_for(64) && kp.dqacc != nullptr)
+        return bf16 ? launch_fused<64, true, false>(kp, tq64, tdo64, tk, tv, stream) : launch_fused<64, false, false>(kp, tq64, tdo64, tk, tv, stream);
     if (kp.d == 128) return bf16 ? launch_tc<128, true>(kp, tq128, tdo128, tq64, tdo64, tk, tv, stream)
                                  : launch_tc<128, false>(kp, tq128, tdo128, tq64, tdo64, tk, tv, stream);
     if (kp.d == 64) return bf16 ? launch_tc<64, true>(kp, tq128, tdo128, tq64, tdo64, tk, tv, stream)
@@ -1239,3 +1271,13 @@ int launch_bwd_tc_sm100(const BwdParams& kp, bool bf16, cudaStream_t stream) {
 }
 
 }  // namespace fa100
+
+#ifdef FA_HANG_GUARD
+extern "C" int fa_b200_hang_read(unsigned int* out8) {   // diagnosis builds only; not part of include/fa_b200.h
+    unsigned int flag = 0;
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(&flag, fa100::g_hang_flag, sizeof(flag));
+    cudaMemcpyFromSymbol(out8, fa100::g_hang_info, 8 * sizeof(unsigned int));
+    return (int)flag;
+}
+#endif

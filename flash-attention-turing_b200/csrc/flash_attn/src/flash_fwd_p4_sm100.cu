@@ -41,7 +41,6 @@ constexpr int kThreadsP4 = 640;                        // a 21st warp does not f
 constexpr int kMma1Warp = 17;                          // MMA issuer of tile 1 (warp 16: tile 0)
 constexpr int kProducerWarp = 18;                      // TMA producer
                                                        // warp 19: TMA store of the O tiles (one staging tile, shared by both query tiles)
-constexpr int kMaxRetry = 40;
 template <int D> struct P4Smem {
     static constexpr int kSlab = kBlockM * 128;          // 64-column slab of a 128-row tile: 16 KB
     static constexpr int kSlabs = D / 64;
@@ -96,17 +95,16 @@ flash_fwd_kernel_sm100_p4(const __grid_constant__ CUtensorMap tmQ, const __grid_
     const uint32_t bar_tok = bar_o_empty + 8 * 2;         // [2]  "tile t's MMA warp may issue its next block"
     const uint32_t tmem_slot = bar_tok + 8 * 2;           // 32-bit words from here on
     const uint32_t stage_lock = tmem_slot + 4;            // the two tiles' epilogues share one staging tile
-    const uint32_t retry_count = stage_lock + 4;          // items whose speculative pass overflowed (see "late-agreed reference")
-    const uint32_t poison = stage_lock + 8;               // [2 tiles][2 item parities]: some row of the tile overflowed in this item
-    const uint32_t retry_list = stage_lock + 24;          // [kMaxRetry] work-item indices, deduplicated at the pass boundary
-    const uint32_t store_desc = retry_list + 4 * kMaxRetry;   // what the staging tile holds {head, first row, batch, item, 2 t + item parity}
+    const uint32_t retry_flag = stage_lock + 4;           // pass 0: some row's speculative step overflowed (see "late-agreed reference")
+    const uint32_t retry_final = stage_lock + 8;          // the flag as published ONCE at the pass boundary: what pass 1 is decided by
+    const uint32_t store_desc = stage_lock + 12;          // what the staging tile holds {head, first row, batch}
     const uint32_t xch = smem + L::kOffXch;
 
     if (warp == 16) {
         if (lane == 0) {
             sts32(stage_lock, 0);
-            sts32(retry_count, 0);
-            for (int i = 0; i < 4; ++i) sts32(poison + 4 * i, 0);
+            sts32(retry_flag, 0);
+            sts32(retry_final, 0);
             for (int t = 0; t < 2; ++t) {
                 mbar_init(bar_q_full + 8 * (t), 1); mbar_init(bar_q_empty + 8 * (t), 1);
                 mbar_init(bar_s_full + 8 * (t), 1);
@@ -129,8 +127,13 @@ flash_fwd_kernel_sm100_p4(const __grid_constant__ CUtensorMap tmQ, const __grid_
     tc_fence_after();
     const uint32_t tmem_base = (uint32_t)lds32(tmem_slot);
 
-    // ---- work list: pass 0 = this CTA's share of the static schedule; pass 1 = the items of pass 0 in which some row's
-    // speculative exponentials overflowed (retry list in shared memory), redone with the exact per-step row max ----
+    // ---- work list: pass 0 = this CTA's share of the static schedule; pass 1 = the same items once more, with the exact
+    // per-step row max, iff some row's speculative exponentials overflowed in pass 0 (one flag per CTA).
+    // Round 2 first kept a per-item retry list that the store warp appended to while it checked per-tile flags; a flag
+    // consumed late changed the list's length WHILE pass 1 was running, the roles read different item counts and the CTA
+    // hung (head_dim 64, fp16, scores of ~N(0, 16^2), three or more items per CTA; found by the random-shape stress,
+    // located with cuda-gdb: profiles/r02_run31_gdb_hang.log).  Nothing pass 1 reads may change while it runs: the decision
+    // is published once, at the pass boundary, and pass 0's flag is never looked at again. ----
     const int slots_mine = (ts.total > (int)blockIdx.x) ? (ts.total - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
     const int n_static = ts.paired ? 2 * slots_mine : slots_mine;      // items of this CTA in the static schedule
     auto static_item = [&](int idx) -> int {                           // idx-th item: slot blockIdx + k gridDim (both halves of a pair)
@@ -138,29 +141,16 @@ flash_fwd_kernel_sm100_p4(const __grid_constant__ CUtensorMap tmQ, const __grid_
     };
     auto pass_count = [&](int pass) -> int {
         if (pass == 0) return n_static;
-        const int c = lds32(retry_count);
-        return c > kMaxRetry ? n_static : c;          // list overflow: redo everything
+        return lds32(retry_final) ? n_static : 0;
     };
     auto pass_item = [&](int pass, int idx) -> int {
-        if (pass == 0 || lds32(retry_count) > kMaxRetry) return static_item(idx);
-        return lds32(retry_list + 4 * idx);
+        (void)pass;
+        return static_item(idx);
     };
     // every thread of the CTA calls this once, between the passes (each role from its own branch: barrier 0 counts threads)
     auto pass_boundary = [&]() {
         __syncthreads();
-        if (tid == 0) {
-            const int c = lds32(retry_count);
-            if (c <= kMaxRetry) {                     // both tiles of an item may have queued it: keep one copy
-                int m = 0;
-                for (int i = 0; i < c; ++i) {
-                    const int v = lds32(retry_list + 4 * i);
-                    bool dup = false;
-                    for (int k2 = 0; k2 < m; ++k2) dup = dup || (lds32(retry_list + 4 * k2) == v);
-                    if (!dup) { sts32(retry_list + 4 * m, v); ++m; }
-                }
-                sts32(retry_count, m);
-            }
-        }
+        if (tid == 0) sts32(retry_final, lds32(retry_flag));
         __syncthreads();
     };
     const bool exact0 = p.exact != 0;                 // FA_B200_FWD_EXACT=1: no speculation at all (A/B runs, debugging)
@@ -380,12 +370,6 @@ flash_fwd_kernel_sm100_p4(const __grid_constant__ CUtensorMap tmQ, const __grid_
                 named_bar_sync(11, 2 * kBlockM + 32);              // staging tile written and fenced by a tile's 256 threads
                 if (lane == 0) {
                     const int bidh = lds32(store_desc), row0 = lds32(store_desc + 4), tb = lds32(store_desc + 8);
-                    const int n = lds32(store_desc + 12), pzi = lds32(store_desc + 16);
-                    if (lds32(poison + 4 * pzi)) {                 // some row of this tile overflowed its speculative step: redo the item
-                        sts32(poison + 4 * pzi, 0);
-                        const int k2 = atoms_add(retry_count, 1);
-                        if (k2 < kMaxRetry) sts32(retry_list + 4 * k2, n);
-                    }
 #pragma unroll
                     for (int sl = 0; sl < kSlabs; ++sl)
                         tma_store_4d(&tmO, sStage + sl * L::kSlab, sl * 64, bidh, row0, tb);
@@ -540,8 +524,8 @@ flash_fwd_kernel_sm100_p4(const __grid_constant__ CUtensorMap tmQ, const __grid_
             // softmax state of the row: reference exponent neg = -m_ref * c2 (identical in both threads of the row), own partial sum
             float neg = 0.f, l_run = 0.f;
             bool has_ref = false;
+            bool overflowed = false;     // some speculative step of this thread overflowed in this item
             hs16 = 0;
-            const uint32_t pz = poison + 4 * (2 * t + (nitem & 1));
 
             // ------------------------------------------------------------------------------------------------------
             // exact step: row max first (pass 1), then the exponentials.  Every step of a retried item, and the first
@@ -745,7 +729,7 @@ flash_fwd_kernel_sm100_p4(const __grid_constant__ CUtensorMap tmQ, const __grid_
                 const float hs = sum.x + sum.y;
                 // overflow (also inf / NaN), or no reference yet (only an exact step can establish one; with prefix masks a row
                 // that saw no key in the first tile sees none at all and never gets here with more than one key step)
-                if (!(hs <= kOverflowAt) || (!has_ref && hs != 0.f)) sts32(pz, 1);
+                overflowed = overflowed || !(hs <= kOverflowAt) || (!has_ref && hs != 0.f);
                 l_run += hs;
             };
             for (int j = 0; j < n_t; ++j) {
@@ -758,6 +742,7 @@ flash_fwd_kernel_sm100_p4(const __grid_constant__ CUtensorMap tmQ, const __grid_
                 }
             }
             its += n_t;
+            if (overflowed) sts32(retry_flag, 1);            // pass 1 redoes the CTA's items with exact steps
 
             // ---- epilogue: O_t / l -> 16 bit -> staging tile (128B-swizzled, the TMA layout) -> TMA store by warp 19 ----
             // Measured alternatives (profiles/r02_run24.log, r02_run25.log): storing O straight from registers with 32-byte
@@ -823,7 +808,6 @@ flash_fwd_kernel_sm100_p4(const __grid_constant__ CUtensorMap tmQ, const __grid_
             if ((tid & 31) == 0) FA_TRACE_EVENT(erole, nitem, 5);
             if (hh == 0 && r_in_tile == 0) {                   // tell the store warp what the staging tile holds
                 sts32(store_desc, w.bidh); sts32(store_desc + 4, g.q_row0 + mt); sts32(store_desc + 8, g.tma_b);
-                sts32(store_desc + 12, n_again); sts32(store_desc + 16, 2 * t + (nitem & 1));
                 __threadfence_block();
             }
             fence_proxy_async_smem();                          // generic-proxy writes -> visible to the TMA engine
@@ -845,11 +829,6 @@ flash_fwd_kernel_sm100_p4(const __grid_constant__ CUtensorMap tmQ, const __grid_
                 }
                 named_bar_sync(tile_bar, 2 * kBlockM);
                 if (hh == 0 && r_in_tile == 0) {
-                    if (lds32(pz)) {                                  // (the store warp does this for whole tiles)
-                        sts32(pz, 0);
-                        const int k2 = atoms_add(retry_count, 1);
-                        if (k2 < kMaxRetry) sts32(retry_list + 4 * k2, n);
-                    }
                     atoms_exch(stage_lock, 0);
                 }
                 __syncwarp();

@@ -80,11 +80,25 @@ template <class B> FA_DEVICE bool mbar_test_wait(B bar, uint32_t parity) {
 // Blocking wait on phase parity.  try_wait is a hardware-suspended wait with a time limit, so the loop
 // spins at most a few times.  With FA_HANG_GUARD the wait traps after ~2^28 polls instead of hanging the
 // GPU box (used in bring-up builds).
+#ifdef FA_HANG_GUARD
+// diagnosis builds: the first wait that exceeds ~0.1 s records who waited on what and every wait of the process gives up
+// (results are garbage, the kernel ends); read back with fa_b200_hang_read() (flash_bwd_tc_sm100.cu)
+static __device__ unsigned int g_hang_flag;
+static __device__ unsigned int g_hang_info[8];
+#endif
 template <class B> FA_DEVICE void mbar_wait(B bar, uint32_t parity) {
 #ifdef FA_HANG_GUARD
-    uint32_t spins = 0;
+    if (mbar_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
     while (!mbar_try_wait(bar, parity)) {
-        if (++spins > (1u << 20)) { asm volatile("trap;"); }
+        if (*(volatile unsigned int*)&g_hang_flag) return;
+        if (clock64() - t0 > 200000000LL) {
+            if (atomicExch(&g_hang_flag, 1u) == 0u) {
+                g_hang_info[0] = smem_u32(bar); g_hang_info[1] = parity; g_hang_info[2] = threadIdx.x;
+                g_hang_info[3] = blockIdx.x; g_hang_info[4] = blockIdx.y; g_hang_info[5] = blockIdx.z;
+            }
+            return;
+        }
     }
 #else
     while (!mbar_try_wait(bar, parity)) {}

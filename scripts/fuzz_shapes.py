@@ -24,6 +24,7 @@ rng = random.Random(seed)
 torch.manual_seed(seed)
 t0 = time.time()
 bad = 0
+verbose = os.environ.get("FUZZ_VERBOSE") == "1"     # print every shape BEFORE it runs (locating a hang)
 for it in range(n):
     d = rng.choice([64, 128])
     dtype = rng.choice([torch.bfloat16, torch.float16])
@@ -44,6 +45,8 @@ for it in range(n):
     k = (torch.randn(b, sk, hk, d, device="cuda") * scale).to(dtype)
     v = torch.randn(b, sk, hk, d, device="cuda").to(dtype)
     tag = f"#{it} b{b} sq{sq} sk{sk} h{h}/{hk} d{d} causal={causal} {dtype} scale={scale}"
+    if verbose:
+        print("FUZZ run", tag, flush=True)
     try:
         o, lse = cabi.fwd(q, k, v, causal)
         do_bwd = rng.random() < 0.4 and scale == 1.0
@@ -56,6 +59,14 @@ for it in range(n):
             assert_close(dq, ref[2], dtype, "dq")
             assert_close(dk, ref[3], dtype, "dk")
             assert_close(dv, ref[4], dtype, "dv")
+        if verbose and hasattr(cabi.load(), "fa_b200_hang_read"):      # hang-guard build (-DFA_HANG_GUARD)
+            import ctypes
+            info = (ctypes.c_uint * 8)()
+            torch.cuda.synchronize()
+            if cabi.load().fa_b200_hang_read(info):
+                print("FUZZ HANG (backward TU)", tag, "barrier", (info[0] - info[6]) // 8, "parity", info[1], "thread", info[2],
+                      "block", info[3], info[4], info[5], flush=True)
+                sys.exit(3)
     except AssertionError as e:
         bad += 1
         print("FUZZ FAIL", tag, str(e)[:300], flush=True)

@@ -1,6 +1,6 @@
 """clock64 timeline of CTA (0,0,0) of the backward's main kernel (instrumented build, see scripts/trace_fwd.py):
 
-    FA_B200_LIB=ab/trace/libfa_b200.so python scripts/trace_bwd.py [b s]
+    FA_B200_LIB=ab/trace/libfa_b200.so python scripts/trace_bwd.py [b s [head_dim]]
 
 role 0 = elementwise thread 0, role 1 = MMA warp; events as stamped by FA_BTRACE in flash_bwd_tc_sm100.cu."""
 import ctypes
@@ -15,8 +15,9 @@ import cabi
 
 b = int(sys.argv[1]) if len(sys.argv) > 1 else 4
 s = int(sys.argv[2]) if len(sys.argv) > 2 else 4096
+d = int(sys.argv[3]) if len(sys.argv) > 3 else 128
 torch.manual_seed(0)
-q, k, v, do = (torch.randn(b, s, 32, 128, device="cuda", dtype=torch.bfloat16) for _ in range(4))
+q, k, v, do = (torch.randn(b, s, 32, d, device="cuda", dtype=torch.bfloat16) for _ in range(4))
 o, lse = cabi.fwd(q, k, v, False)
 for _ in range(2):
     cabi.bwd(q, k, v, o, lse, do, False)
@@ -27,7 +28,7 @@ buf = (ctypes.c_longlong * words)()
 lib.fa_b200_trace_read.argtypes = [ctypes.POINTER(ctypes.c_longlong), ctypes.c_int]
 assert lib.fa_b200_trace_read(buf, words) == 0, "not a trace build"
 t0 = min(x for x in buf if x > 0)
-print(f"BTRACE bwd b{b} s{s}: role step : events (cycles since the first stamp)")
+print(f"BTRACE bwd b{b} s{s} d{d}: role step : events (cycles since the first stamp)")
 for r in range(2):
     for j in range(0, 12):
         ev = [buf[(r * 64 + j) * 8 + e] for e in range(8)]

@@ -60,15 +60,15 @@ def test_bwd_validates_gradient_pointers():
 
 
 def test_bwd_workspace_bytes_is_the_fused_backward_accumulator():
-    """host-only: the fp32 dQ accumulator [b][h][ceil64(seqlen_q)][d] for head_dim 128 (fused backward), nothing for 64"""
+    """host-only: the fp32 dQ accumulator [b][h][ceil64(seqlen_q)][d] of the fused backward, head_dim 128 and 64"""
     import os
     lib = cabi.load()
-    if os.environ.get("FA_B200_BWD", "fused")[0] != "f":
-        pytest.skip("FA_B200_BWD selects a non-fused backward")
+    if os.environ.get("FA_B200_BWD", "fused")[0] != "f" or os.environ.get("FA_B200_BWD_D64", "fused")[0] != "f":
+        pytest.skip("FA_B200_BWD / FA_B200_BWD_D64 select a non-fused backward")
     p = _params(b=3, seqlen_q=130, h=6, h_k=2, d=128)
     assert lib.fa_b200_bwd_workspace_bytes(ctypes.byref(p)) == 3 * 6 * 192 * 128 * 4
     p = _params(b=3, seqlen_q=130, h=6, h_k=2, d=64)
-    assert lib.fa_b200_bwd_workspace_bytes(ctypes.byref(p)) == 0
+    assert lib.fa_b200_bwd_workspace_bytes(ctypes.byref(p)) == 3 * 6 * 192 * 64 * 4
     assert lib.fa_b200_bwd_workspace_bytes(None) == 0
 
 
