@@ -36,7 +36,7 @@ struct BwdParams {
 int launch_bwd_tc_sm100(const BwdParams& kp, bool bf16, cudaStream_t stream);
 
 // Fused backward (default; FA_B200_BWD=det switches it off): one K/V-stationary kernel produces dK, dV and — through fp32
-// bulk reductions into the workspace — dQ.  head_dim 128 only; needs a workspace of bwd_fused_workspace_bytes(); a caller
+// bulk reductions into the workspace — dQ.  head_dim 128 and 64 (FA_B200_BWD_D64=det keeps 64 on the two kernels); needs a workspace of bwd_fused_workspace_bytes(); a caller
 // that passes no workspace gets the deterministic two-kernel path.
 bool bwd_fused_enabled();
 long long bwd_fused_workspace_bytes(long long b, long long sq_max, long long h, long long d);

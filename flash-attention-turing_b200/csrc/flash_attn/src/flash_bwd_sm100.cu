@@ -4,7 +4,7 @@
 // flash_bwd_kernel.h:28-838 (dQ) and :842-1676 (dK/dV): recompute P = exp(S*scale - LSE), dP = dO V^T,
 // dS = P * (dP - D); dQ = scale * dS K; dK = scale * dS^T Q; dV = P^T dO.
 // Determinism: dK and dV are bit-reproducible on every path.  dQ is bit-reproducible on the two-kernel path (no
-// workspace, or FA_B200_BWD=det) like the reference; the default fused path for head_dim 128 accumulates dQ with fp32
+// workspace, or FA_B200_BWD=det) like the reference; the default fused path (head_dim 128 and 64) accumulates dQ with fp32
 // reductions (red.global.add / cp.reduce.async.bulk) whose order varies from run to run (last-bit differences).
 // GQA: the reference writes per-q-head dK/dV into h-expanded buffers and reduces with torch::sum_out
 // (flash_api.cpp:265-312); here the group sum happens inside the dK/dV kernel.

@@ -71,7 +71,7 @@ typedef struct fa_bwd_params {
     void* dv;                   /* dv_ptr   needs h-expanded buffers + torch::sum_out, flash_api.cpp:265-312) */
     float* dsum;                /* do_o_ptr: scratch fp32 [b, h, seqlen_q] = rowsum(dO * O) */
     void* workspace;            /* device scratch of fa_b200_bwd_workspace_bytes() bytes: the fp32 dQ accumulator of the
-                                   fused backward (head_dim 128).  NULL is always allowed: the library then runs the two
+                                   fused backward (head_dim 128 and 64).  NULL is always allowed: the library then runs the two
                                    deterministic kernels (dQ, dK/dV) that mirror the reference's structure */
 } fa_bwd_params;
 

@@ -14,6 +14,7 @@ import flash_attn_turing as fat
 ap = argparse.ArgumentParser()
 ap.add_argument("--dtype", default="fp16")
 ap.add_argument("--quick", action="store_true")
+ap.add_argument("--hdim", type=int, default=0, help="only this head_dim (0 = both, as benchmark.sh:20)")
 args = ap.parse_args()
 dt = torch.float16 if args.dtype == "fp16" else torch.bfloat16
 batch_size, num_heads = 4, 16                                          # benchmark.sh:17-19
@@ -42,7 +43,7 @@ print(f"benchmark.sh grid (batch {batch_size}, heads {num_heads}), dtype {args.d
 print(f"| seqlen | hdim | causal | flash_fwd_kernel ms | TFLOP/s | flash_bwd (dot+dq+dk_dv) ms | TFLOP/s | torch SDPA fwd ms | TFLOP/s | torch SDPA bwd ms | TFLOP/s | reference kernels fwd ms | bwd ms |")
 print("|---|---|---|---|---|---|---|---|---|---|---|---|---|")
 for s in seqlens:
-    for d in (64, 128):
+    for d in ((args.hdim,) if args.hdim else (64, 128)):
         for causal in (False, True):
             torch.manual_seed(0)
             q = torch.randn(batch_size, s, num_heads, d, device="cuda", dtype=dt); k = torch.randn_like(q); v = torch.randn_like(q); do = torch.randn_like(q)
