@@ -10,7 +10,7 @@ Headline workload (`value`, `config.workload`):
   N = 1 : BASELINE.json configs[1] ("C2": b4 s4096 h32 d128 bf16 forward, non-causal) — the configuration `metric` is
           quoted on.  The same line also carries, each timed in its own loop with its own clock samples:
             sustained : C2 again in a >= 2 s loop (the 1 kW power cap governs; fraction of the sustained peak)
-            configs   : C3 (b4 s8192 causal), C4fwd, C4bwd (b4 s16384 forward / backward), C5shard (b32 s16384: one
+            configs   : C3 (b4 s8192 causal), C4fwd, C4bwd (b4 s16384 forward / backward), D64fwd, D64bwd (b4 s4096 head_dim 64), C5shard (b32 s16384: one
                         rank's slab of config 5)
   N > 1 : the same C2 workload on every rank (b=4 per rank, seed 1000 + rank; batch x head problems shard with no
           collective on the data path), so scaling is "weak" in the contract's sense — per-GPU work is the N=1 work — and
@@ -60,6 +60,7 @@ CONFIGS = {
     "C3": (4, 8192, 32, 128, True, "bs=4 seq=8192 heads=32 hdim=128 bf16 causal forward"),
     "C4fwd": (4, 16384, 32, 128, False, "bs=4 seq=16384 heads=32 hdim=128 bf16 forward (fwd half of config 4)"),
     "C5shard": (32, 16384, 32, 128, False, "bs=256/8 seq=16384 heads=32 hdim=128 bf16 forward, one rank's batch shard of config 5"),
+    "D64": (4, 4096, 32, 64, False, "bs=4 seq=4096 heads=32 hdim=64 bf16 forward (the reference's other head_dim, benchmark.sh:20)"),
 }
 METRIC = "attention fwd TFLOP/s at head_dim=128; % of B200 bf16 tensor-core peak"
 CPU_SLICE_HEADS = 4
@@ -321,6 +322,34 @@ def main():
                "algorithmic_bytes_per_step": fwd_bytes(cb, cs, ch, cd)}
         return leg, (q, k, v, o, lse)
 
+    def bwd_leg(name, tensors, steps, desc):
+        """backward of CONFIGS[name] through the C ABI on the forward leg's tensors: dot(dO,O) + fused dK/dV/dQ + dQ convert"""
+        cb, cs, ch, cd, ccausal, _ = CONFIGS[name]
+        qb, kb, vb, ob, lb = tensors
+        dob = torch.randn_like(qb)
+        dqb, dkb, dvb, dsb = torch.empty_like(qb), torch.empty_like(kb), torch.empty_like(vb), torch.empty_like(lb)
+        bp = cabi.BwdParams()
+        bp.fwd = cabi.make_fwd_params(qb, kb, vb, ob, lb, ccausal)
+        bp.dout, bp.dq, bp.dk, bp.dv, bp.dsum = dob.data_ptr(), dqb.data_ptr(), dkb.data_ptr(), dvb.data_ptr(), dsb.data_ptr()
+        nbytes = int(lib.fa_b200_bwd_workspace_bytes(ctypes.byref(bp.fwd)))
+        ws = torch.empty(max(nbytes, 1), device=dev, dtype=torch.uint8)
+        bp.workspace = ws.data_ptr() if nbytes > 0 else None
+
+        def bstep():
+            rc = lib.fa_b200_bwd(ctypes.byref(bp), sptr)
+            if rc != 0:
+                raise RuntimeError(lib.fa_b200_last_error().decode())
+
+        bstep()
+        bl = lib.fa_b200_last_launch_count()
+        msb, _, nb, clk = time_loop(bstep, steps, 2)
+        flb = 2.5 * fwd_flops(cb, cs, ch, cd, ccausal)
+        tfb = flb / (msb * 1e-3) / 1e12
+        return {"workload": desc, "value": tfb, "unit": "TFLOP/s (algorithmic 2.5x fwd)", "ms_per_step": msb, "steps": nb,
+                "frac_of_burst_peak": tfb / peaks["burst"],
+                "frac_of_sustained_peak": tfb / peaks["sustained"] if peaks["sustained"] else None,
+                "timed_region_ms": msb * nb, "gpu_launches": bl * nb, "clocks": clk}
+
     # ---------------- headline ----------------
     head, (q, k, v, o, lse) = fwd_leg(cfg_name, args.steps, args.warmup)
     ms_per_step, value = head["ms_per_step"], head["value"]
@@ -342,32 +371,16 @@ def main():
                     leg, (q4, k4, v4, o4, l4) = fwd_leg(name, st, 3)
                     legs[name] = leg
                     # config 4's backward half: dot(dO,O) + fused dK/dV/dQ kernel + dQ convert, through the C ABI
-                    do4 = torch.randn_like(q4)
-                    dq4, dk4, dv4, ds4 = torch.empty_like(q4), torch.empty_like(k4), torch.empty_like(v4), torch.empty_like(l4)
-                    bp = cabi.BwdParams()
-                    bp.fwd = cabi.make_fwd_params(q4, k4, v4, o4, l4, False)
-                    bp.dout, bp.dq, bp.dk, bp.dv, bp.dsum = do4.data_ptr(), dq4.data_ptr(), dk4.data_ptr(), dv4.data_ptr(), ds4.data_ptr()
-                    nbytes = int(lib.fa_b200_bwd_workspace_bytes(ctypes.byref(bp.fwd)))
-                    ws = torch.empty(max(nbytes, 1), device=dev, dtype=torch.uint8)
-                    bp.workspace = ws.data_ptr() if nbytes > 0 else None
-
-                    def bstep():
-                        rc = lib.fa_b200_bwd(ctypes.byref(bp), sptr)
-                        if rc != 0:
-                            raise RuntimeError(lib.fa_b200_last_error().decode())
-
-                    bstep()
-                    bl = lib.fa_b200_last_launch_count()
-                    msb, _, nb, clk = time_loop(bstep, 5, 2)
-                    flb = 2.5 * fwd_flops(*CONFIGS["C4fwd"][:5])
-                    legs["C4bwd"] = {"workload": "C4 backward: bs=4 seq=16384 heads=32 hdim=128 bf16 (dO.O + fused dK/dV/dQ + dQ convert)",
-                                     "value": flb / (msb * 1e-3) / 1e12, "unit": "TFLOP/s (algorithmic 2.5x fwd)", "ms_per_step": msb,
-                                     "steps": nb, "frac_of_burst_peak": flb / (msb * 1e-3) / 1e12 / peaks["burst"],
-                                     "frac_of_sustained_peak": flb / (msb * 1e-3) / 1e12 / peaks["sustained"] if peaks["sustained"] else None,
-                                     "timed_region_ms": msb * nb, "gpu_launches": bl * nb, "clocks": clk}
-                    del q4, k4, v4, o4, l4, do4, dq4, dk4, dv4, ds4, ws
+                    legs["C4bwd"] = bwd_leg("C4fwd", (q4, k4, v4, o4, l4), 5,
+                                            "C4 backward: bs=4 seq=16384 heads=32 hdim=128 bf16 (dO.O + fused dK/dV/dQ + dQ convert)")
+                    del q4, k4, v4, o4, l4
                 else:
                     legs[name], _ = fwd_leg(name, st, 3)
+                torch.cuda.empty_cache()
+            if cfg_name != "D64":      # head_dim 64: forward and backward (fused dK/dV/dQ kernel with an M = 64 dQ^T)
+                legs["D64fwd"], t64 = fwd_leg("D64", 20, 3)
+                legs["D64bwd"] = bwd_leg("D64", t64, 10, "D64 backward: bs=4 seq=4096 heads=32 hdim=64 bf16 (dO.O + fused dK/dV/dQ + dQ convert)")
+                del t64
                 torch.cuda.empty_cache()
             if cfg_name != "C5shard":
                 try:
