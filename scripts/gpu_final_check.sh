@@ -1,19 +1,22 @@
 #!/bin/bash
-# final validation of the committed defaults on one B200: GPU tests, smoke, the driver's bench line, the C5 shard config
+# validation of the committed defaults on one B200: GPU tests, smoke, the driver's bench line (all legs), the reference arm
+#   gpurun --timeout 700 -- 'bash scripts/gpu_final_check.sh'     (~3 min of box time)
 set -u
-mkdir -p gpurun_out
-exec > >(tee -a gpurun_out/final.log) 2>&1
-timeout 300 python -c "import torch; torch.zeros(1).cuda(); print('torch warm')"
-echo "== pytest -m gpu"
-timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -5
-echo "== smoke"
+O=gpurun_out/final; mkdir -p $O
+exec > >(tee -a $O/final.log) 2>&1
+t0=$(date +%s); stamp() { echo "== $* (t+$(( $(date +%s) - t0 )) s)"; }
+stamp "pytest -m gpu"
+timeout 600 python -m pytest tests -m gpu -x -q 2>&1 | tail -6
+stamp smoke
 timeout 200 python -c "import __graft_entry__ as g; g.smoke()"
-echo "== bench (default flags)"
-timeout 500 python bench.py > gpurun_out/bench_final.json 2> gpurun_out/bench_final.err; tail -1 gpurun_out/bench_final.json | cut -c1-1500
-echo "== bench --bwd C4"
-timeout 500 python bench.py --config C4fwd --steps 10 --bwd --no-cpu-baseline --no-e2e 2>/dev/null | tail -1 | python -c "
-import json,sys; j=json.loads(sys.stdin.read()); print('C4 fwd', round(j['value'],1), 'bwd', round(j['bwd']['ms_per_step'],2), round(j['bwd']['value'],1), j['clocks'])"
-echo "== C5 shard (b=32 s=16384), 2 steps"
-timeout 500 python bench.py --config C5shard --steps 2 --warmup 3 --no-cpu-baseline --no-e2e 2>/dev/null | tail -1 | python -c "
-import json,sys; j=json.loads(sys.stdin.read()); print('C5shard fwd', round(j['value'],1), 'ms', round(j['ms_per_step'],2), j['clocks'])"
-echo "== done"
+stamp "bench (default flags)"
+timeout 500 python bench.py > $O/bench_n1.json 2> $O/bench_n1.err; tail -c 300 $O/bench_n1.err
+python - <<PY
+import json
+j = json.loads(open("$O/bench_n1.json").read().strip().splitlines()[-1])
+print("value", round(j["value"], 1), "frac", round(j["roofline"]["frac"], 3), "sustained", round(j["sustained"]["value"], 1),
+      {k: round(v["value"], 1) for k, v in j["configs"].items()}, "e2e", round(j["e2e"]["value"], 1), j["clocks"])
+PY
+stamp "reference arm"
+timeout 300 python bench.py --impl reference --steps 5 --warmup 3 > $O/bench_ref.json; cut -c1-300 $O/bench_ref.json
+stamp done
