@@ -1,4 +1,5 @@
 #!/bin/bash
+# (round-1 evidence script, kept for the history of profiles/r01*: it uses the bench flags of that time — `--bwd` is gone, the backward legs are configs.C4bwd / D64bwd of the default line now; see scripts/gpu_final_check.sh)
 set -u
 mkdir -p gpurun_out
 exec > >(tee -a gpurun_out/run13.log) 2>&1

@@ -1,4 +1,5 @@
 #!/bin/bash
+# (round-1 evidence script, kept for the history of profiles/r01*: it uses the bench flags of that time — `--bwd` is gone, the backward legs are configs.C4bwd / D64bwd of the default line now; see scripts/gpu_final_check.sh)
 # evidence run: bench lines (C2 default + bwd, C3, C4fwd + bwd, 200-step sustained), ncu launch list of the bench command,
 # one ncu --set full capture of the forward kernel
 set -u
