@@ -16,12 +16,12 @@
 // cycles per row-tile against 1050-1150 with two, profiles/r01_ubench_softmax_pipes.log).
 //
 // Key loop of a softmax thread (details at key_step / spec_step below):
-//   * exact step (first step of an item, every step of a retried item): row max of the thread's 64 scores, exchanged with
+//   * exact step (first step of an item, every step of pass 1): row max of the thread's 64 scores, exchanged with
 //     the peer thread of the row through a 4-byte shared-memory slot and a 64-thread named barrier; lazy reference (moves
 //     only when the max grows by > 2^8); then the exponentials.
 //   * speculative step (all others): exponentials against the reference agreed so far; the two threads of a row publish
-//     their step sums and read each other's one step late ("late-agreed reference"); an overflow inside one key tile flags
-//     the item and the CTA redoes it with exact steps in a second pass.
+//     their step sums and read each other's one step late ("late-agreed reference"); an overflow inside one key tile raises
+//     the CTA's retry flag and the CTA walks its items once more with exact steps (pass 1).
 //   * P leaves in four 16-column quarters per thread (TMEM store, then one elected arrive per warp half a chunk later);
 //     the MMA warp issues P V in the same order, k-steps (q, 4+q) for quarter q.
 // P quarter q of half hh overwrites columns [64hh + 8q, +8) of S_t, which have been consumed by then.
@@ -528,7 +528,7 @@ flash_fwd_kernel_sm100_p4(const __grid_constant__ CUtensorMap tmQ, const __grid_
             hs16 = 0;
 
             // ------------------------------------------------------------------------------------------------------
-            // exact step: row max first (pass 1), then the exponentials.  Every step of a retried item, and the first
+            // exact step: row max first, then the exponentials.  Every step of the retry pass (pass 1), and the first
             // step of every item.
             // ------------------------------------------------------------------------------------------------------
             auto key_step = [&](auto mask_tag, const int j) {
@@ -655,7 +655,8 @@ flash_fwd_kernel_sm100_p4(const __grid_constant__ CUtensorMap tmQ, const __grid_
             // arithmetic on identical inputs -> identical reference, no vote) and rescale their half of O and their partial
             // l — an exact power of two.  What cannot be fixed one step late is an overflow inside a single key tile
             // (bf16: a row sum above 2^100, fp16: above 2^15, i.e. scores jumping by that much within 128 keys): the thread
-            // flags the item, its rows come out as garbage, and the CTA redoes the whole item with exact steps in pass 1.
+            // raises the CTA's retry flag (after the key loop), its rows come out as garbage, and pass 1 redoes the CTA's items
+            // with exact steps.
             // ------------------------------------------------------------------------------------------------------
             auto spec_step = [&](auto mask_tag, const int j) {
                 constexpr bool need_mask = decltype(mask_tag)::value;
