@@ -3,6 +3,9 @@ drops or duplicates tiles.  Mirrors (line for line, in Python integers):
   * decode_item / make_tile_sched   (flash_fwd_common.cuh): the persistent forward's static work list
   * item_geom's per-tile key-block counts vs the element-wise causal rule j - i <= sk - sq (mask.h:20-72 in the reference)
   * the fused backward's rotated walk over the 64-row query sub-tiles (flash_bwd_tc_sm100.cu: it0, steps_per_head, rot, q_sub)
+  * the forward's role protocol in COUNTS (flash_fwd_p4_sm100.cu): tokens given / taken by the two MMA warps, K/V ring releases
+    per tile and warp, Q loads vs waits, staged tiles the store warp expects vs the softmax slots hand over — a mismatch there
+    is a hang, not a wrong number
 """
 import itertools
 import random
@@ -217,3 +220,91 @@ def test_fastdiv_matches_integer_division_below_2_31():
             if 0 <= n < 2 ** 31:
                 q = n if d == 1 else ((n * mul) >> 32) >> shr
                 assert q == n // d, (n, d, q, n // d)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# The forward's role protocol in counts (flash_fwd_p4_sm100.cu): every role walks the same item list and derives, from the
+# item's geometry alone, how many times it will wait on / arrive at each barrier.  A mismatch is a hang, not a wrong number
+# (the retry-list hang of round 2 was exactly that: roles that disagreed about the list).  Restated here per item:
+#   tokens     (0,j) takes iff j >= 1 and j-1 < nb1, gives iff j < nb1;  (1,j) takes iff j < nb0, gives iff j+1 < nb0
+#   K/V ring   every tile of the item (2 * max(nb0, nb1)) is released exactly once by EACH MMA warp (commit or plain arrive)
+#   Q buffers  the producer loads Q_t iff nb_t > 0; MMA warp t waits for it iff nb_t > 0
+#   hand-over  the store warp expects one staged tile per (item, t) with rows and keys; the softmax slot t hands over the same
+#   S / P      softmax slot t waits for nb_t score tiles and arrives 4 quarters each; MMA warp t issues nb_t S and waits 4 nb_t quarters
+# ------------------------------------------------------------------------------------------------------------------
+def _item_protocol_counts(nb0, nb1):
+    nb = (nb0, nb1)
+    takes, gives = [0, 0], [0, 0]
+    for j in range(nb0):                                   # MMA warp of tile 0
+        takes[0] += (j >= 1 and j - 1 < nb1)
+        gives[0] += (j < nb1)                              # wakes (1, j)
+    for j in range(nb1):                                   # MMA warp of tile 1
+        takes[1] += (j < nb0)
+        gives[1] += (j + 1 < nb0)                          # wakes (0, j + 1)
+    nbmax = max(nb)
+    releases = []
+    for t in range(2):
+        rel = [0] * (2 * nbmax)                            # ring tiles of the item: K_j = 2 j, V_j = 2 j + 1
+        if nb[t] > 0:
+            rel[0] += 1                                    # K_0 right after S(0)
+        for j in range(nb[t]):
+            rel[2 * j + 1] += 1                            # V_j after block j
+            if j + 1 < nb[t]:
+                rel[2 * j + 2] += 1                        # K_j+1 after S(j+1)
+        for j in range(nb[t], nbmax):                      # tiles only the other query tile needs
+            rel[2 * j] += 1
+            rel[2 * j + 1] += 1
+        releases.append(rel)
+    return takes, gives, releases
+
+
+def test_forward_role_protocol_counts_are_consistent_for_every_block_count_pair():
+    for nb0, nb1 in itertools.product(range(0, 12), repeat=2):
+        takes, gives, releases = _item_protocol_counts(nb0, nb1)
+        assert gives[0] == takes[1], (nb0, nb1, "tokens passed to tile 1's MMA warp")
+        assert gives[1] == takes[0], (nb0, nb1, "tokens passed to tile 0's MMA warp")
+        for t in range(2):
+            assert all(c == 1 for c in releases[t]), (nb0, nb1, t, releases[t])   # count-2 barrier: one arrival per warp and use
+
+
+def test_every_role_derives_the_same_work_from_an_item():
+    """producer, the two MMA warps, the softmax slots and the store warp all decode (item -> geometry) themselves; what they
+    conclude has to agree for every item of every CTA, in pass 0 and — the same static list again — in the retry pass."""
+    random.seed(1)
+    shapes = [(5, 8, 2211, 1202, 64, True), (6, 8, 2070, 1777, 64, False), (4, 16, 2275, 1261, 64, True), (2, 4, 300, 333, 128, True),
+              (1, 2, 1, 1, 64, False), (3, 4, 1025, 1, 128, True), (2, 2, 129, 4000, 128, False)]
+    shapes += [(random.randint(1, 6), random.randint(1, 12), random.randint(1, 2600), random.randint(1, 2600), random.choice([64, 128]),
+                random.random() < 0.5) for _ in range(150)]
+    for b, h, sq, sk, d, causal in shapes:
+        ts = make_tile_sched(b, h, sq, sk, d, 16, causal)
+        grid = min(ts["total"], 148)
+        for cta in range(grid):
+            q_loads, q_waits, stores, handovers, s_issued, s_waited = [0, 0], [0, 0], 0, 0, [0, 0], [0, 0]
+            kv_loaded = kv_released = 0
+            for n in cta_items(ts, cta, grid):
+                mblk, _, _ = decode_item(ts, n, h, causal)
+                m0 = mblk * 256
+                if m0 >= sq:                               # g.skip: every role skips the item
+                    continue
+                nb = [nblk(m0 + 128 * t, sq, sk, causal) for t in range(2)]
+                n_blocks = max(nb)
+                if n_blocks > 0:                           # producer and MMA warps (they skip items without keys)
+                    kv_loaded += 2 * n_blocks
+                    _, _, releases = _item_protocol_counts(nb[0], nb[1])
+                    kv_released += sum(releases[0])
+                    assert sum(releases[0]) == sum(releases[1]) == 2 * n_blocks
+                for t in range(2):
+                    mt = m0 + 128 * t
+                    has_rows = mt < sq
+                    if n_blocks > 0 and nb[t] > 0:
+                        q_loads[t] += 1                    # producer: load_q(t)
+                        q_waits[t] += 1                    # MMA warp t: bar_q_full
+                        s_issued[t] += nb[t]
+                    if has_rows and nb[t] > 0:             # softmax slot t: key loop + epilogue
+                        s_waited[t] += nb[t]
+                        handovers += 1
+                    if not (mt >= sq or nb[t] == 0):       # store warp's count (dense: every such tile is a whole TMA tile)
+                        stores += 1
+                    assert not (nb[t] > 0 and not has_rows), "a tile without rows never has key blocks"
+            assert q_loads == q_waits and s_issued == s_waited and stores == handovers and kv_loaded == kv_released, \
+                (b, h, sq, sk, d, causal, cta)
